@@ -1,0 +1,225 @@
+// am_fft.cuh -- register-resident Stockham FFT building block (sm_100a).
+//
+// Every thread keeps 16 complex values in registers for the whole transform;
+// shared memory is only the exchange medium between stages (one write + one
+// read per stage boundary).  Radices are 2/4/8/16 chosen so that a length
+// 2^LOG2N transform takes ceil(LOG2N/4) stages.  The same code serves
+//   * row transforms      (BATCH = 1, one contiguous row per thread group)
+//   * column-tile transforms (BATCH = T columns, element (i,t) at i*T+t)
+// The inverse transform runs the forward plan backwards, so the registers a
+// thread holds after the forward transform's last stage are exactly the inputs
+// of the inverse transform's first stage (no exchange across the spectrum
+// multiply) and the inverse's outputs land on the indices the thread loaded.
+//
+// The phase functions are __host__ __device__ so tests/host_emul.cu can run the
+// identical index arithmetic on the CPU (this container has no GPU).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef AM_HD
+#define AM_HD __host__ __device__ __forceinline__
+#endif
+
+namespace amfft {
+
+constexpr int EPT = 16;           // complex elements per thread
+constexpr int TW_LOG2 = 14;       // master twiddle table: W_{2^14}^j, j < 2^14
+constexpr int TW_N = 1 << TW_LOG2;
+
+AM_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+AM_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a*conj(b)
+AM_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+AM_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV> AM_HD float2 mul_mi(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+// multiply by compile-time twiddle exp(-+ 2 pi i j/16) given as (c, s) = (cos, sin) of the angle magnitude
+template <bool INV> AM_HD float2 mul_w(float2 a, float c, float s) {
+    // forward: (c - i s); inverse: (c + i s)
+    return INV ? make_float2(a.x * c - a.y * s, a.y * c + a.x * s) : make_float2(a.x * c + a.y * s, a.y * c - a.x * s);
+}
+
+#define AM_C8 0.70710678118654752440f
+#define AM_C16_1 0.92387953251128675613f
+#define AM_S16_1 0.38268343236508977173f
+
+template <bool INV> AM_HD void dft2(float2 &a, float2 &b) {
+    float2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+// in-place natural-order 4-point DFT
+template <bool INV> AM_HD void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
+    float2 s0 = cadd(a0, a2), d0 = csub(a0, a2), s1 = cadd(a1, a3), d1 = mul_mi<INV>(csub(a1, a3));
+    a0 = cadd(s0, s1);
+    a1 = cadd(d0, d1);
+    a2 = csub(s0, s1);
+    a3 = csub(d0, d1);
+}
+// 8 = 4 x 2: n = 2 n1 + n2, k = k1 + 4 k2
+template <bool INV> AM_HD void dft8(float2 *v) {
+    dft4<INV>(v[0], v[2], v[4], v[6]);    // n2 = 0 -> A[k1][0] in v[0],v[2],v[4],v[6]
+    dft4<INV>(v[1], v[3], v[5], v[7]);    // n2 = 1 -> A[k1][1] in v[1],v[3],v[5],v[7]
+    v[3] = mul_w<INV>(v[3], AM_C8, AM_C8);            // W8^1
+    v[5] = mul_mi<INV>(v[5]);                          // W8^2
+    v[7] = mul_w<INV>(v[7], -AM_C8, AM_C8);           // W8^3
+    float2 x0 = cadd(v[0], v[1]), x4 = csub(v[0], v[1]);
+    float2 x1 = cadd(v[2], v[3]), x5 = csub(v[2], v[3]);
+    float2 x2 = cadd(v[4], v[5]), x6 = csub(v[4], v[5]);
+    float2 x3 = cadd(v[6], v[7]), x7 = csub(v[6], v[7]);
+    v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3; v[4] = x4; v[5] = x5; v[6] = x6; v[7] = x7;
+}
+// 16 = 4 x 4: n = 4 n1 + n2, k = k1 + 4 k2
+template <bool INV> AM_HD void dft16(float2 *v) {
+    dft4<INV>(v[0], v[4], v[8], v[12]);   // n2 = 0: A[k1][0] at v[4 k1 + 0]
+    dft4<INV>(v[1], v[5], v[9], v[13]);
+    dft4<INV>(v[2], v[6], v[10], v[14]);
+    dft4<INV>(v[3], v[7], v[11], v[15]);
+    // twiddle A[k1][n2] *= W16^{n2 k1}
+    v[5] = mul_w<INV>(v[5], AM_C16_1, AM_S16_1);      // 1
+    v[6] = mul_w<INV>(v[6], AM_C8, AM_C8);            // 2
+    v[7] = mul_w<INV>(v[7], AM_S16_1, AM_C16_1);      // 3
+    v[9] = mul_w<INV>(v[9], AM_C8, AM_C8);            // 2
+    v[10] = mul_mi<INV>(v[10]);                        // 4
+    v[11] = mul_w<INV>(v[11], -AM_C8, AM_C8);         // 6
+    v[13] = mul_w<INV>(v[13], AM_S16_1, AM_C16_1);    // 3
+    v[14] = mul_w<INV>(v[14], -AM_C8, AM_C8);         // 6
+    v[15] = mul_w<INV>(v[15], -AM_C16_1, -AM_S16_1);  // 9: cos(9pi/8) = -c1, sin(9pi/8) = -s1
+    // second step: for each k1, DFT4 over n2: X[k1 + 4 k2]
+    dft4<INV>(v[0], v[1], v[2], v[3]);
+    dft4<INV>(v[4], v[5], v[6], v[7]);
+    dft4<INV>(v[8], v[9], v[10], v[11]);
+    dft4<INV>(v[12], v[13], v[14], v[15]);
+    // v[4 k1 + k2] holds X[k1 + 4 k2]: transpose to natural order
+    float2 t;
+#define AM_SWAP(a, b) t = v[a]; v[a] = v[b]; v[b] = t;
+    AM_SWAP(1, 4) AM_SWAP(2, 8) AM_SWAP(3, 12) AM_SWAP(6, 9) AM_SWAP(7, 13) AM_SWAP(11, 14)
+#undef AM_SWAP
+}
+template <int R, bool INV> AM_HD void dft(float2 *v) {
+    if constexpr (R == 2) dft2<INV>(v[0], v[1]);
+    else if constexpr (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
+    else if constexpr (R == 8) dft8<INV>(v);
+    else dft16<INV>(v);
+}
+
+// v[r] *= w^r, r = 1..R-1, with w^r built by a depth-log2(R) product tree
+template <int R> AM_HD void apply_twiddle_powers(float2 *v, float2 w1) {
+    v[1] = cmul(v[1], w1);
+    if constexpr (R >= 4) {
+        float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        if constexpr (R >= 8) {
+            float2 w4 = cmul(w2, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+            v[4] = cmul(v[4], w4); v[5] = cmul(v[5], w5); v[6] = cmul(v[6], w6); v[7] = cmul(v[7], w7);
+            if constexpr (R >= 16) {
+                float2 w8 = cmul(w4, w4);
+                v[8] = cmul(v[8], w8);
+                v[9] = cmul(v[9], cmul(w8, w1));   v[10] = cmul(v[10], cmul(w8, w2));
+                v[11] = cmul(v[11], cmul(w8, w3)); v[12] = cmul(v[12], cmul(w8, w4));
+                v[13] = cmul(v[13], cmul(w8, w5)); v[14] = cmul(v[14], cmul(w8, w6));
+                v[15] = cmul(v[15], cmul(w8, w7));
+            }
+        }
+    }
+}
+
+// Transform plan: LOG2N = length, LOG2B = batch (columns interleaved), INV = direction.
+// GT = threads in the group that owns the N*B elements (N*B == 16*GT).
+template <int LOG2N, int LOG2B, bool INV> struct RegFFT {
+    static constexpr int N = 1 << LOG2N, B = 1 << LOG2B;
+    static constexpr int GT = (N * B) / EPT;
+    static constexpr int NST = (LOG2N + 3) / 4;
+    static_assert(LOG2N >= 4 && LOG2N <= TW_LOG2, "unsupported length");
+    static_assert(N * B >= EPT, "group too small");
+    // radix bits of stage st in execution order (inverse = forward plan reversed)
+    static constexpr int bits_at(int st) {
+        int s = INV ? NST - 1 - st : st;
+        return LOG2N / NST + (s < LOG2N % NST ? 1 : 0);
+    }
+    static constexpr int logns_at(int st) {          // log2 of the product of the radices before stage st
+        int a = 0;
+        for (int i = 0; i < st; ++i) a += bits_at(i);
+        return a;
+    }
+    // padded shared-memory slot of flat element index i (i = idx*B + t)
+    static AM_HD int slot(int i) { return B >= 16 ? i : i + (i >> 4); }
+    static constexpr int SMEM_ELEMS = (B >= 16) ? N * B : N * B + ((N * B) >> 4);
+
+    // element index (within the length-N transform) that register j holds BEFORE stage st,
+    // and the batch column: used by callers for the first stage's loads.
+    template <int ST> static AM_HD void in_coord(int gtid, int j, int &idx, int &t) {
+        constexpr int RB = bits_at(ST), R = 1 << RB;
+        int l = j >> RB, r = j & (R - 1);
+        int id = gtid + l * GT;
+        t = id & (B - 1);
+        idx = (id >> LOG2B) + r * (N >> RB);
+    }
+    // element index register j holds AFTER the last stage (natural order output index)
+    static AM_HD void out_coord(int gtid, int j, int &idx, int &t) {
+        constexpr int RB = bits_at(NST - 1), R = 1 << RB;
+        int l = j >> RB, s = j & (R - 1);
+        int id = gtid + l * GT;
+        t = id & (B - 1);
+        idx = (id >> LOG2B) + s * (N >> RB);
+    }
+
+    // twiddle + butterflies of stage ST on the registers
+    template <int ST> static AM_HD void butterfly(float2 (&v)[EPT], int gtid, const float2 *__restrict__ tw) {
+        constexpr int RB = bits_at(ST), R = 1 << RB, NB = EPT / R, LOGNS = logns_at(ST);
+#pragma unroll
+        for (int l = 0; l < NB; ++l) {
+            if constexpr (ST > 0) {
+                int q = (gtid + l * GT) >> LOG2B;
+                int k = q & ((1 << LOGNS) - 1);
+                float2 w = tw[k << (TW_LOG2 - LOGNS - RB)];          // W_{Ns R}^k
+                if (INV) w.y = -w.y;
+                apply_twiddle_powers<R>(&v[l * R], w);
+            }
+            dft<R, INV>(&v[l * R]);
+        }
+    }
+    // scatter stage ST's outputs into the exchange buffer (Stockham autosort index)
+    template <int ST> static AM_HD void xchg_write(const float2 (&v)[EPT], float2 *sm, int gtid) {
+        constexpr int RB = bits_at(ST), R = 1 << RB, NB = EPT / R, LOGNS = logns_at(ST);
+#pragma unroll
+        for (int l = 0; l < NB; ++l) {
+            int id = gtid + l * GT;
+            int t = id & (B - 1), q = id >> LOG2B;
+            int k = q & ((1 << LOGNS) - 1);
+            int base = ((q - k) << RB) + k;
+#pragma unroll
+            for (int s = 0; s < R; ++s) sm[slot(((base + (s << LOGNS)) << LOG2B) + t)] = v[l * R + s];
+        }
+    }
+    // gather the inputs of stage ST (ST >= 1) from the exchange buffer
+    template <int ST> static AM_HD void xchg_read(float2 (&v)[EPT], const float2 *sm, int gtid) {
+        constexpr int RB = bits_at(ST), R = 1 << RB, NB = EPT / R;
+#pragma unroll
+        for (int l = 0; l < NB; ++l) {
+            int id = gtid + l * GT;
+            int t = id & (B - 1), q = id >> LOG2B;
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[l * R + r] = sm[slot(((q + r * (N >> RB)) << LOG2B) + t)];
+        }
+    }
+
+#ifdef __CUDACC__
+    // Full transform on the device.  On entry v holds the stage-0 inputs (see in_coord<0>),
+    // on exit the natural-order outputs (see out_coord).  All threads of the CTA must call.
+    template <int ST = 0> static __device__ __forceinline__ void run(float2 (&v)[EPT], float2 *sm, int gtid,
+                                                                     const float2 *__restrict__ tw) {
+        butterfly<ST>(v, gtid, tw);
+        if constexpr (ST + 1 < NST) {
+            xchg_write<ST>(v, sm, gtid);
+            __syncthreads();
+            xchg_read<ST + 1>(v, sm, gtid);
+            __syncthreads();
+            run<ST + 1>(v, sm, gtid, tw);
+        }
+    }
+#endif
+};
+
+}  // namespace amfft

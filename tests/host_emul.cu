@@ -1,0 +1,134 @@
+// host_emul.cu -- runs the register-FFT phase functions of am_fft.cuh on the CPU
+// (threads become loop iterations, __syncthreads becomes a phase boundary) and
+// checks them against a double-precision DFT.  Built and run by
+// tests/test_host_emul.py with `nvcc -x cu` as a host-only program: this is how
+// the index arithmetic of the CUDA kernels is verified in a container with no GPU.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../audio_matcher_b200/csrc/am_fft.cuh"
+
+using namespace amfft;
+typedef std::complex<double> cd;
+
+static void ref_fft(std::vector<cd> &a, bool inv) {   // recursive radix-2, double
+    size_t n = a.size();
+    if (n == 1) return;
+    std::vector<cd> e(n / 2), o(n / 2);
+    for (size_t i = 0; i < n / 2; ++i) { e[i] = a[2 * i]; o[i] = a[2 * i + 1]; }
+    ref_fft(e, inv); ref_fft(o, inv);
+    for (size_t k = 0; k < n / 2; ++k) {
+        double ang = (inv ? 2.0 : -2.0) * M_PI * (double)k / (double)n;
+        cd w(cos(ang), sin(ang));
+        a[k] = e[k] + w * o[k];
+        a[k + n / 2] = e[k] - w * o[k];
+    }
+}
+
+static std::vector<float2> g_tw;
+
+template <class F, int ST> struct Runner {
+    static void go(std::vector<float2> &regs, std::vector<float2> &sm) {
+        constexpr int GT = F::GT;
+        for (int t = 0; t < GT; ++t) F::template butterfly<ST>(*(float2(*)[EPT]) & regs[t * EPT], t, g_tw.data());
+        if constexpr (ST + 1 < F::NST) {
+            for (int t = 0; t < GT; ++t) F::template xchg_write<ST>(*(const float2(*)[EPT]) & regs[t * EPT], sm.data(), t);
+            for (int t = 0; t < GT; ++t) F::template xchg_read<ST + 1>(*(float2(*)[EPT]) & regs[t * EPT], sm.data(), t);
+            Runner<F, ST + 1>::go(regs, sm);
+        }
+    }
+};
+
+template <int LOG2N, int LOG2B, bool INV> static double check() {
+    typedef RegFFT<LOG2N, LOG2B, INV> F;
+    constexpr int N = F::N, B = F::B, GT = F::GT;
+    std::vector<float2> x(N * B);
+    srand(1234 + LOG2N * 31 + LOG2B);
+    for (auto &e : x) e = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+    std::vector<float2> regs(GT * EPT), sm(F::SMEM_ELEMS, make_float2(NAN, NAN));
+    for (int t = 0; t < GT; ++t)
+        for (int j = 0; j < EPT; ++j) {
+            int idx, c;
+            F::template in_coord<0>(t, j, idx, c);
+            regs[t * EPT + j] = x[idx * B + c];
+        }
+    Runner<F, 0>::go(regs, sm);
+    std::vector<float2> y(N * B, make_float2(NAN, NAN));
+    for (int t = 0; t < GT; ++t)
+        for (int j = 0; j < EPT; ++j) {
+            int idx, c;
+            F::out_coord(t, j, idx, c);
+            y[idx * B + c] = regs[t * EPT + j];
+        }
+    double maxerr = 0, maxref = 0;
+    for (int c = 0; c < B; ++c) {
+        std::vector<cd> a(N);
+        for (int i = 0; i < N; ++i) a[i] = cd(x[i * B + c].x, x[i * B + c].y);
+        ref_fft(a, INV);
+        for (int i = 0; i < N; ++i) {
+            double e = std::abs(a[i] - cd(y[i * B + c].x, y[i * B + c].y));
+            if (!(e <= maxerr)) maxerr = e;          // NaN-propagating max
+            maxref = std::max(maxref, std::abs(a[i]));
+        }
+    }
+    double rel = maxerr / maxref;
+    printf("fft log2n=%d log2b=%d inv=%d stages=%d  max_rel_err=%.3g %s\n", LOG2N, LOG2B, (int)INV, F::NST, rel,
+           rel < 2e-6 ? "OK" : "FAIL");
+    return rel;
+}
+
+// the forward-then-inverse register hand-over used by the row kernel: after the forward
+// transform the thread multiplies its registers and feeds them to the inverse unchanged.
+template <int LOG2N> static double check_roundtrip() {
+    typedef RegFFT<LOG2N, 0, false> F;
+    typedef RegFFT<LOG2N, 0, true> I;
+    constexpr int N = F::N, GT = F::GT;
+    std::vector<float2> x(N);
+    for (auto &e : x) e = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+    std::vector<float2> regs(GT * EPT), sm(F::SMEM_ELEMS);
+    double bad = 0;
+    for (int t = 0; t < GT; ++t)
+        for (int j = 0; j < EPT; ++j) {
+            int idx, c, idx2, c2;
+            F::template in_coord<0>(t, j, idx, c);
+            regs[t * EPT + j] = x[idx];
+            // coordinates must line up: fwd out == inv in, inv out == fwd in
+            F::out_coord(t, j, idx, c); I::template in_coord<0>(t, j, idx2, c2);
+            if (idx != idx2) bad = 1;
+            F::template in_coord<0>(t, j, idx, c); I::out_coord(t, j, idx2, c2);
+            if (idx != idx2) bad = 1;
+        }
+    Runner<F, 0>::go(regs, sm);
+    Runner<I, 0>::go(regs, sm);
+    double maxerr = 0;
+    for (int t = 0; t < GT; ++t)
+        for (int j = 0; j < EPT; ++j) {
+            int idx, c;
+            I::out_coord(t, j, idx, c);
+            double ex = regs[t * EPT + j].x / N - x[idx].x, ey = regs[t * EPT + j].y / N - x[idx].y;
+            maxerr = std::max(maxerr, std::sqrt(ex * ex + ey * ey));
+        }
+    printf("roundtrip log2n=%d coord_mismatch=%d max_err=%.3g %s\n", LOG2N, (int)bad, maxerr,
+           (bad == 0 && maxerr < 2e-6) ? "OK" : "FAIL");
+    return bad ? 1.0 : maxerr;
+}
+
+int main() {
+    g_tw.resize(TW_N);
+    for (int j = 0; j < TW_N; ++j) {
+        double a = -2.0 * M_PI * j / TW_N;
+        g_tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    double worst = 0;
+#define CHK(n, b) worst = std::max(worst, check<n, b, false>()); worst = std::max(worst, check<n, b, true>());
+    CHK(4, 0) CHK(5, 0) CHK(6, 0) CHK(7, 0) CHK(8, 0) CHK(9, 0) CHK(10, 0) CHK(11, 0) CHK(12, 0) CHK(13, 0) CHK(14, 0)
+    CHK(4, 4) CHK(5, 4) CHK(6, 4) CHK(7, 4) CHK(8, 4) CHK(9, 4) CHK(10, 4) CHK(4, 2) CHK(6, 3) CHK(9, 5)
+    worst = std::max(worst, check_roundtrip<4>());
+    worst = std::max(worst, check_roundtrip<9>());
+    worst = std::max(worst, check_roundtrip<13>());
+    printf(worst < 2e-6 ? "ALL OK\n" : "SOME FAILED\n");
+    return worst < 2e-6 ? 0 : 1;
+}

@@ -1,0 +1,810 @@
+// am_capi.cu -- C ABI (include/audio_matcher.h) and host-side scheduling of the matcher.
+//
+// Host responsibilities (everything numeric runs in the CUDA kernels):
+//   * plan: overlap-save block length N, four-step split N1 x N2, segments of logical chunks
+//   * stage host-resident PCM to the device through two buffers on a copy stream
+//   * launch K2/K4/K5 (or the single-pass kernel) per group of block pairs, then the
+//     per-chunk peak kernels; one D2H of the peak list at the end
+//   * calc_chunks' tail: stable sort by start + filter_surrounding/is_overshadowed
+//     (src/matcher/audio_matcher.rs:132-160) over the handful of surviving peaks
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/audio_matcher.h"
+#include "am_kernels.cuh"
+#include "am_peaks.cuh"
+
+static_assert(sizeof(am_peak) == sizeof(amp::DevPeak), "am_peak layout");
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+am_status fail(am_status st, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return st;
+}
+
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? AM_ERR_NOMEM : AM_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+    } while (0)
+#define TRY(expr)                       \
+    do {                                \
+        am_status s_ = (expr);          \
+        if (s_ != AM_OK) return s_;     \
+    } while (0)
+
+size_t env_mb(const char *name, size_t dflt_mb) {
+    const char *v = getenv(name);
+    if (v && *v) {
+        long long x = atoll(v);
+        if (x > 0) return (size_t)x;
+    }
+    return dflt_mb;
+}
+
+int ceil_log2(unsigned long long x) {
+    int l = 0;
+    while ((1ull << l) < x) ++l;
+    return l;
+}
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    am_status reserve(size_t want) {
+        if (want <= n) return AM_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        CU(cudaMalloc((void **)&p, want * sizeof(T)));
+        n = want;
+        return AM_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace
+
+struct am_matcher {
+    std::mutex mu;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    am_config cfg;
+    uint32_t sr = 0;
+    size_t m = 0;
+    DevBuf<float> d_snip;
+    double sumsq = 0.0;
+    float inv_ac = 0.f;
+    DevBuf<float2> d_tw;
+    std::map<int, float2 *> spectra;
+    DevBuf<float2> d_A;
+    DevBuf<float> d_c, d_tmin, d_tmax;
+    DevBuf<amp::DevPeak> d_peaks;
+    DevBuf<unsigned long long> d_count;   // [0] = count, [1] low 32 bits = flags
+    DevBuf<unsigned char> d_stage[2];
+    am_stats stats;
+    // optional per-kernel-class device timing (cudaEvent pairs around every launch)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<int> ev_cls;                 // class of event pair i (events 2i, 2i+1)
+    double cls_ms[AM_KERNEL_CLASSES] = {0};
+    uint64_t cls_launches[AM_KERNEL_CLASSES] = {0};
+};
+
+namespace {
+
+size_t fmt_bytes(int fmt) { return fmt == AM_FMT_F32_MONO ? 4 : (fmt == AM_FMT_I16_MONO ? 2 : 4); }
+
+template <class K> am_status set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return AM_OK;
+}
+
+cudaEvent_t prof_event(am_matcher *h) {
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        h->ev_pool.push_back(e);
+    }
+    return h->ev_pool[h->ev_used++];
+}
+void prof_begin(am_matcher *h, int cls) {
+    if (!h->profiling) return;
+    h->ev_cls.push_back(cls);
+    cudaEventRecord(prof_event(h), h->stream);
+}
+void prof_end(am_matcher *h) {
+    if (!h->profiling) return;
+    cudaEventRecord(prof_event(h), h->stream);
+}
+// after the stream has been synchronised: fold the recorded event pairs into the class totals
+void prof_collect(am_matcher *h) {
+    for (size_t i = 0; i < h->ev_cls.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]) == cudaSuccess) {
+            h->cls_ms[h->ev_cls[i]] += ms;
+            h->cls_launches[h->ev_cls[i]]++;
+        }
+    }
+    h->ev_cls.clear();
+    h->ev_used = 0;
+}
+
+#define LAUNCH(h, cls, ...)                    \
+    do {                                       \
+        prof_begin((h), (cls));                \
+        __VA_ARGS__;                           \
+        prof_end((h));                         \
+        (h)->stats.kernel_launches++;          \
+        CU(cudaGetLastError());                \
+    } while (0)
+
+// ---- kernel dispatch ----------------------------------------------------------------
+template <int LOG2N, int MODE> am_status launch_small_t(am_matcher *h, const amk::BlockGroup &g, float2 *spec) {
+    typedef amk::SmallCfg<LOG2N> Cfg;
+    TRY(set_smem(amk::k_small<LOG2N, MODE>, Cfg::SMEM));
+    int pairs = (g.nblocks + 1) / 2;
+    int grid = (pairs + Cfg::G - 1) / Cfg::G;
+    LAUNCH(h, AM_K_SMALL, amk::k_small<LOG2N, MODE><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, spec, h->d_tw.p));
+    return AM_OK;
+}
+template <int MODE> am_status launch_small(am_matcher *h, int log2n, const amk::BlockGroup &g, float2 *spec) {
+    switch (log2n) {
+#define C_(L) case L: return launch_small_t<L, MODE>(h, g, spec);
+        C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13)
+#undef C_
+    }
+    return fail(AM_ERR_UNSUPPORTED, "single-pass length 2^%d not built", log2n);
+}
+
+template <int L1, bool INV> am_status launch_col_t(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *A) {
+    typedef amk::ColCfg<L1> Cfg;
+    int pairs = (g.nblocks + 1) / 2;
+    dim3 grid((1u << l2) >> Cfg::LT, pairs);
+    if (INV) {
+        TRY(set_smem(amk::k_col_inv<L1>, Cfg::SMEM));
+        LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
+    } else {
+        TRY(set_smem(amk::k_col_fwd<L1>, Cfg::SMEM));
+        LAUNCH(h, AM_K_COL_FWD, amk::k_col_fwd<L1><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
+    }
+    return AM_OK;
+}
+template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::BlockGroup &g, int l2, float2 *A) {
+    switch (l1) {
+#define C_(L) case L: return launch_col_t<L, INV>(h, g, l2, A);
+        C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11)
+#undef C_
+    }
+    return fail(AM_ERR_UNSUPPORTED, "column length 2^%d not built", l1);
+}
+
+template <int L2, int MODE> am_status launch_row_t(am_matcher *h, float2 *A, float2 *spec, int l1, int rows) {
+    typedef amk::RowCfg<L2> Cfg;
+    TRY(set_smem(amk::k_row<L2, MODE>, Cfg::SMEM));
+    int grid = (rows + Cfg::G - 1) / Cfg::G;
+    LAUNCH(h, AM_K_ROW, amk::k_row<L2, MODE><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(A, spec, l1, rows, h->d_tw.p));
+    return AM_OK;
+}
+template <int MODE> am_status launch_row(am_matcher *h, int l2, float2 *A, float2 *spec, int l1, int rows) {
+    switch (l2) {
+#define C_(L) case L: return launch_row_t<L, MODE>(h, A, spec, l1, rows);
+        C_(10) C_(11) C_(12) C_(13)
+#undef C_
+    }
+    return fail(AM_ERR_UNSUPPORTED, "row length 2^%d not built", l2);
+}
+
+// ---- planning -----------------------------------------------------------------------
+constexpr int SMALL_MAX_LOG2 = 13;
+constexpr int MAX_LOG2 = 24;
+
+void split(int log2n, int &l1, int &l2) {
+    if (log2n <= SMALL_MAX_LOG2) { l1 = 0; l2 = log2n; return; }
+    l2 = std::min(13, log2n - 4);
+    const char *v = getenv("AM_ROW_LOG2");
+    if (v && *v) {
+        int x = atoi(v);
+        if (x >= 10 && x <= 13 && log2n - x >= 4 && log2n - x <= 11) l2 = x;
+    }
+    l1 = log2n - l2;
+    if (l1 > 11) { l1 = 11; l2 = log2n - 11; }
+}
+
+am_status choose_log2n(const am_matcher *h, unsigned long long outputs, int &log2n) {
+    const unsigned long long m = h->m;
+    if (h->cfg.fft_log2) {
+        log2n = (int)h->cfg.fft_log2;
+        if (log2n < 4 || log2n > MAX_LOG2) return fail(AM_ERR_INVALID, "fft_log2 %d outside [4, %d]", log2n, MAX_LOG2);
+        if ((1ull << log2n) < 2 * m) return fail(AM_ERR_INVALID, "fft_log2 %d too small for a snippet of %llu samples", log2n, m);
+        return AM_OK;
+    }
+    int l = std::max(8, ceil_log2(8 * m));
+    if (l > 23) l = std::max(23, ceil_log2(2 * m));
+    if (l > MAX_LOG2) return fail(AM_ERR_UNSUPPORTED, "snippet of %llu samples needs an FFT block > 2^%d", m, MAX_LOG2);
+    while (l > 4 && (1ull << (l - 1)) >= 2 * m && (1ull << (l - 1)) - m + 1 >= outputs) --l;
+    log2n = l;
+    return AM_OK;
+}
+
+amk::StreamView snippet_view(const am_matcher *h) {
+    amk::StreamView sv;
+    sv.x = h->d_snip.p;
+    sv.fmt = amk::FMT_F32_MONO;
+    sv.buf_first = 0;
+    sv.buf_frames = (long long)h->m;
+    sv.total = (long long)h->m;
+    sv.lead = 0;
+    return sv;
+}
+
+am_status ensure_workspace(am_matcher *h, int log2n, unsigned long long pairs_total, unsigned long long &pairs_per_group) {
+    size_t budget = env_mb("AM_WORKSPACE_MB", 1024) << 20;
+    size_t per_pair = sizeof(float2) << log2n;
+    unsigned long long g = std::max<size_t>(1, budget / per_pair);
+    g = std::min<unsigned long long>(g, pairs_total);
+    g = std::min<unsigned long long>(g, 32768);
+    TRY(h->d_A.reserve((size_t)g << log2n));
+    pairs_per_group = g;
+    return AM_OK;
+}
+
+// conjugate spectrum of the zero-padded snippet for block length 2^log2n, computed once per
+// matcher in double precision on the device and stored as correctly rounded fp32 in the order
+// the row kernel consumes ([k1][k2] for the four-step split)
+am_status get_spectrum(am_matcher *h, int log2n, float2 **out) {
+    auto it = h->spectra.find(log2n);
+    if (it != h->spectra.end()) { *out = it->second; return AM_OK; }
+    const long long n = 1ll << log2n;
+    int l1, l2;
+    split(log2n, l1, l2);
+    float2 *spec = nullptr;
+    double2 *buf = nullptr;
+    CU(cudaMalloc((void **)&spec, sizeof(float2) << log2n));
+    cudaError_t e = cudaMalloc((void **)&buf, 2 * (sizeof(double2) << log2n));
+    if (e != cudaSuccess) { cudaFree(spec); return fail(AM_ERR_NOMEM, "spectrum scratch: %s", cudaGetErrorString(e)); }
+    double2 *a = buf, *b = buf + n;
+    const unsigned grid_n = (unsigned)((n + 255) / 256), grid_h = (unsigned)((n / 2 + 255) / 256);
+    prof_begin(h, AM_K_SPECTRUM);
+    amk::k_spec64_load<<<grid_n, 256, 0, h->stream>>>(snippet_view(h), n, a);
+    h->stats.kernel_launches++;
+    for (long long ns = 1; ns < n; ns <<= 1) {
+        amk::k_spec64_pass<<<grid_h, 256, 0, h->stream>>>(a, b, n / 2, ns);
+        h->stats.kernel_launches++;
+        std::swap(a, b);
+    }
+    amk::k_spec64_store<<<grid_n, 256, 0, h->stream>>>(a, n, l1, l1 ? l2 : 0, spec);
+    h->stats.kernel_launches++;
+    prof_end(h);
+    e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(buf);
+    if (e != cudaSuccess) { cudaFree(spec); return fail(AM_ERR_CUDA, "snippet spectrum: %s", cudaGetErrorString(e)); }
+    h->spectra[log2n] = spec;
+    *out = spec;
+    return AM_OK;
+}
+
+// correlation outputs [g0, g1) (virtual offsets) -> c[g - c_g0]
+am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0, long long g1, int log2n,
+                          float scalar, float *c, long long c_g0) {
+    if (g1 <= g0) return AM_OK;
+    if (h->m <= (size_t)amk::DIRECT_MAX_M && !getenv("AM_NO_DIRECT")) {
+        // very short snippet: direct sums; `scalar` carries 1/N for the transform paths
+        const float sc = scalar * (float)(1ull << log2n);
+        const unsigned long long nb = (unsigned long long)(g1 - g0 + 255) / 256;
+        if (nb > 0x7fffffffull) return fail(AM_ERR_UNSUPPORTED, "direct path: too many outputs");
+        LAUNCH(h, AM_K_DIRECT, amk::k_direct<<<(unsigned)nb, 256, 0, h->stream>>>(sv, h->d_snip.p, (int)h->m, g0, g1, c, c_g0, sc));
+        h->stats.fft_log2 = 0; h->stats.log2_n1 = 0; h->stats.log2_n2 = 0;
+        return AM_OK;
+    }
+    float2 *spec;
+    TRY(get_spectrum(h, log2n, &spec));
+    const long long N = 1ll << log2n, VN = N - (long long)h->m + 1;
+    const unsigned long long nblocks = (unsigned long long)((g1 - g0 + VN - 1) / VN);
+    const unsigned long long pairs_total = (nblocks + 1) / 2;
+    int l1, l2;
+    split(log2n, l1, l2);
+    h->stats.fft_log2 = log2n; h->stats.log2_n1 = l1; h->stats.log2_n2 = l2;
+    h->stats.fft_blocks += nblocks;
+    amk::BlockGroup g;
+    g.sv = sv; g.g_end = g1; g.VN = VN; g.c = c; g.c_g0 = c_g0; g.scalar = scalar;
+    unsigned long long ppg = 1u << 20;     // pairs per launch
+    if (l1 != 0) TRY(ensure_workspace(h, log2n, pairs_total, ppg));
+    for (unsigned long long p0 = 0; p0 < pairs_total; p0 += ppg) {
+        unsigned long long np = std::min(ppg, pairs_total - p0);
+        g.g0 = g0 + (long long)(2 * p0) * VN;
+        g.nblocks = (int)std::min<unsigned long long>(2 * np, nblocks - 2 * p0);
+        if (l1 == 0) {
+            TRY(launch_small<0>(h, log2n, g, spec));
+        } else {
+            TRY(launch_col<false>(h, l1, g, l2, h->d_A.p));
+            TRY(launch_row<0>(h, l2, h->d_A.p, spec, l1, (int)(np << l1)));
+            TRY(launch_col<true>(h, l1, g, l2, h->d_A.p));
+        }
+    }
+    return AM_OK;
+}
+
+am_status init_common(am_matcher *h, uint32_t sr, const am_config *cfg) {
+    CU(cudaGetDevice(&h->device));
+    h->sr = sr;
+    if (cfg) h->cfg = *cfg; else am_config_default(&h->cfg);
+    if (h->cfg.overlap_s < 0) h->cfg.overlap_s = (double)h->m / (double)sr;
+    if (!(h->cfg.chunk_size_s > 0)) return fail(AM_ERR_INVALID, "chunk_size_s must be > 0");
+    memset(&h->stats, 0, sizeof h->stats);
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+    // master twiddle table W_{2^14}^j from double precision
+    std::vector<float2> tw(amfft::TW_N);
+    for (int j = 0; j < amfft::TW_N; ++j) {
+        double a = -2.0 * M_PI * (double)j / (double)amfft::TW_N;
+        tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    TRY(h->d_tw.reserve(amfft::TW_N));
+    CU(cudaMemcpy(h->d_tw.p, tw.data(), sizeof(float2) * amfft::TW_N, cudaMemcpyHostToDevice));
+    TRY(h->d_count.reserve(2));
+    // sum s^2 on the device (double accumulation)
+    double *d_acc = (double *)h->d_count.p;
+    CU(cudaMemsetAsync(d_acc, 0, sizeof(double), h->stream));
+    LAUNCH(h, AM_K_SPECTRUM, amk::k_sumsq<<<(unsigned)std::min<size_t>(1024, (h->m + 255) / 256), 256, 0, h->stream>>>(snippet_view(h), (long long)h->m, d_acc));
+    CU(cudaMemcpyAsync(&h->sumsq, d_acc, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->inv_ac = (float)(1.0 / h->sumsq);
+    return AM_OK;
+}
+
+// Duration::from_secs_f64(start / sr) truncated to whole nanoseconds (src/matcher/mod.rs:127-129)
+uint64_t start_ns(uint64_t start, uint32_t sr) {
+    double v = (double)start / (double)sr;
+    if (!(v > 0.0)) return 0;
+    int e;
+    double fr = frexp(v, &e);
+    uint64_t mant = (uint64_t)ldexp(fr, 53);
+    e -= 53;
+    unsigned __int128 t = (unsigned __int128)mant * 1000000000ull;
+    if (e >= 0) return (uint64_t)(t << e);
+    if (-e >= 127) return 0;
+    return (uint64_t)(t >> (-e));
+}
+uint64_t duration_ns(double secs) { return secs <= 0 ? 0 : (uint64_t)llround(secs * 1e9); }
+
+// ---- synthetic workload generator (bench/test utility) -------------------
+__device__ __forceinline__ unsigned long long hash64(unsigned long long seed, unsigned long long n) {
+    unsigned long long z = seed + n * 0x9E3779B97F4A7C15ull;     // SplitMix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void k_synth_pcm16(unsigned long long seed, unsigned long long first, size_t count, short *out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (short)((int)(hash64(seed, first + i) >> 50) - 8192);
+}
+__global__ void k_synth_plant(short *pcm, size_t frames, int channels, const short *snip, size_t m,
+                              unsigned long long offset, int shift) {
+    size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    size_t f = offset + j;
+    if (f >= frames) return;
+    for (int ch = 0; ch < channels; ++ch) {
+        int v = (pcm[f * channels + ch] >> 1) + (snip[j] >> shift);
+        v = v > 32767 ? 32767 : (v < -32768 ? -32768 : v);
+        pcm[f * channels + ch] = (short)v;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *am_last_error(void) { return g_err; }
+int am_abi_version(void) { return AM_ABI_VERSION; }
+int am_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void am_config_default(am_config *cfg) {
+    if (!cfg) return;
+    cfg->chunk_size_s = 60.0;       // src/matcher/args.rs:71
+    cfg->overlap_s = -1.0;          // snippet duration, audio_matcher.rs:41
+    cfg->distance_s = 480.0;        // src/matcher/args.rs:75
+    cfg->prominence = 0.13f;        // 13 / 100, args.rs:19 + audio_matcher.rs:44
+    cfg->fft_log2 = 0;
+    cfg->max_peaks_per_chunk = 0;
+    cfg->reserved = 0;
+}
+
+size_t am_out_len(size_t n, size_t m, am_mode mode) {
+    if (n == 0 || m == 0) return 0;
+    switch (mode) {
+    case AM_MODE_FULL: return n + m - 1;
+    case AM_MODE_SAME: return n;
+    default: return n >= m ? n - m + 1 : 0;
+    }
+}
+
+static am_status create_impl(const void *data, size_t m, int fmt, uint32_t sr, const am_config *cfg, am_matcher **out) {
+    if (!out) return fail(AM_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!data || m == 0) return fail(AM_ERR_INVALID, "empty snippet");
+    if (sr == 0) return fail(AM_ERR_INVALID, "sample rate 0");
+    if (m > (1ull << (MAX_LOG2 - 1))) return fail(AM_ERR_UNSUPPORTED, "snippet of %zu samples exceeds 2^%d", m, MAX_LOG2 - 1);
+    if (am_device_count() == 0) return fail(AM_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
+    am_matcher *h = new (std::nothrow) am_matcher();
+    if (!h) return fail(AM_ERR_NOMEM, "out of host memory");
+    h->m = m;
+    am_status st = h->d_snip.reserve(m);
+    if (st == AM_OK) {
+        if (fmt == AM_FMT_F32_MONO) {
+            cudaError_t e = cudaMemcpy(h->d_snip.p, data, m * sizeof(float), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) st = fail(AM_ERR_CUDA, "snippet upload: %s", cudaGetErrorString(e));
+        } else {
+            // scale / downmix on the device with the same load path the stream uses
+            void *raw = nullptr;
+            size_t bytes = m * fmt_bytes(fmt);
+            cudaError_t e = cudaMalloc(&raw, bytes);
+            if (e == cudaSuccess) e = cudaMemcpy(raw, data, bytes, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                amk::StreamView sv{raw, fmt, 0, (long long)m, (long long)m, 0};
+                amk::k_to_f32<<<(unsigned)((m + 255) / 256), 256>>>(sv, 0, (long long)m, h->d_snip.p);
+                e = cudaDeviceSynchronize();
+            }
+            if (raw) cudaFree(raw);
+            if (e != cudaSuccess) st = fail(AM_ERR_CUDA, "snippet upload: %s", cudaGetErrorString(e));
+        }
+    }
+    if (st == AM_OK) st = init_common(h, sr, cfg);
+    if (st != AM_OK) { am_matcher_destroy(h); return st; }
+    *out = h;
+    return AM_OK;
+}
+
+am_status am_matcher_create(const float *snippet, size_t m, uint32_t sr, const am_config *cfg, am_matcher **out) {
+    return create_impl(snippet, m, AM_FMT_F32_MONO, sr, cfg, out);
+}
+am_status am_matcher_create_pcm16(const int16_t *pcm, size_t frames, int channels, uint32_t sr, const am_config *cfg,
+                                  am_matcher **out) {
+    if (channels != 1 && channels != 2) return fail(AM_ERR_INVALID, "channels must be 1 or 2");
+    return create_impl(pcm, frames, channels == 2 ? AM_FMT_I16_STEREO : AM_FMT_I16_MONO, sr, cfg, out);
+}
+
+void am_matcher_destroy(am_matcher *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto &kv : h->spectra) cudaFree(kv.second);
+    h->d_snip.release(); h->d_tw.release(); h->d_A.release(); h->d_c.release(); h->d_tmin.release();
+    h->d_tmax.release(); h->d_peaks.release(); h->d_count.release();
+    h->d_stage[0].release(); h->d_stage[1].release();
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    delete h;
+}
+
+am_status am_matcher_set_stream(am_matcher *h, void *cuda_stream) {
+    if (!h) return fail(AM_ERR_INVALID, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->stream = (cudaStream_t)cuda_stream;
+    return AM_OK;
+}
+am_status am_matcher_set_config(am_matcher *h, const am_config *cfg) {
+    if (!h || !cfg) return fail(AM_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!(cfg->chunk_size_s > 0)) return fail(AM_ERR_INVALID, "chunk_size_s must be > 0");
+    h->cfg = *cfg;
+    if (h->cfg.overlap_s < 0) h->cfg.overlap_s = (double)h->m / (double)h->sr;
+    return AM_OK;
+}
+am_status am_matcher_get_stats(const am_matcher *h, am_stats *out) {
+    if (!h || !out) return fail(AM_ERR_INVALID, "NULL argument");
+    *out = h->stats;
+    return AM_OK;
+}
+
+am_status am_matcher_set_profiling(am_matcher *h, int on) {
+    if (!h) return fail(AM_ERR_INVALID, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->profiling = on != 0;
+    for (int i = 0; i < AM_KERNEL_CLASSES; ++i) { h->cls_ms[i] = 0; h->cls_launches[i] = 0; }
+    return AM_OK;
+}
+am_status am_matcher_get_kernel_times(const am_matcher *h, am_kernel_time *out, size_t cap, size_t *n_out) {
+    static const char *names[AM_KERNEL_CLASSES] = {"k_col_fwd", "k_row", "k_col_inv", "k_small", "k_direct",
+                                                   "k_tile_minmax", "k_chunk_peaks", "spectrum"};
+    if (!h || !n_out || (!out && cap)) return fail(AM_ERR_INVALID, "NULL argument");
+    size_t k = 0;
+    for (int i = 0; i < AM_KERNEL_CLASSES; ++i) {
+        if (!h->cls_launches[i]) continue;
+        if (k < cap) {
+            out[k].kernel_class = i;
+            out[k].launches = h->cls_launches[i];
+            out[k].total_ms = h->cls_ms[i];
+            strncpy(out[k].name, names[i], sizeof out[k].name - 1);
+            out[k].name[sizeof out[k].name - 1] = 0;
+        }
+        ++k;
+    }
+    *n_out = k;
+    return AM_OK;
+}
+
+am_status am_inverse_sample_auto_correlation(am_matcher *h, float *out) {
+    if (!h || !out) return fail(AM_ERR_INVALID, "NULL argument");
+    *out = h->inv_ac;
+    return AM_OK;
+}
+
+am_status am_correlate(am_matcher *h, const void *within, size_t n, am_sample_fmt fmt, am_mem within_mem,
+                       am_mode mode, int scale, float *out, size_t cap, am_mem out_mem, size_t *out_len) {
+    if (!h || !out_len) return fail(AM_ERR_INVALID, "NULL argument");
+    if ((int)fmt < 0 || (int)fmt > 2 || (int)mode < 0 || (int)mode > 2) return fail(AM_ERR_INVALID, "bad fmt/mode");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    memset(&h->stats, 0, sizeof h->stats);
+    const size_t olen = am_out_len(n, h->m, mode);
+    *out_len = olen;
+    if (olen == 0) return AM_OK;
+    if (!within || !out) return fail(AM_ERR_INVALID, "NULL buffer");
+    if (olen > cap) return fail(AM_ERR_CAPACITY, "output needs %zu floats, capacity %zu", olen, cap);
+    amk::StreamView sv;
+    sv.fmt = (int)fmt; sv.buf_first = 0; sv.buf_frames = (long long)n; sv.total = (long long)n;
+    const long long full = (long long)(n + h->m - 1);
+    sv.lead = (long long)(h->m - 1) - (full - (long long)olen) / 2;      // centered(): audio_matcher.rs:460-464
+    if (within_mem == AM_MEM_HOST) {
+        size_t bytes = n * fmt_bytes(fmt);
+        TRY(h->d_stage[0].reserve(bytes));
+        CU(cudaMemcpyAsync(h->d_stage[0].p, within, bytes, cudaMemcpyHostToDevice, h->stream));
+        h->stats.h2d_bytes += bytes;
+        sv.x = h->d_stage[0].p;
+    } else sv.x = within;
+    float *d_out = out;
+    if (out_mem == AM_MEM_HOST) {
+        TRY(h->d_c.reserve(olen));
+        d_out = h->d_c.p;
+    }
+    int log2n;
+    TRY(choose_log2n(h, olen, log2n));
+    const float scalar = (float)(1.0 / (double)(1ull << log2n)) * (scale ? h->inv_ac : 1.0f);
+    TRY(run_correlation(h, sv, 0, (long long)olen, log2n, scalar, d_out, 0));
+    if (out_mem == AM_MEM_HOST) {
+        CU(cudaMemcpyAsync(out, d_out, olen * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        h->stats.d2h_bytes += olen * sizeof(float);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    prof_collect(h);
+    h->stats.frames = n;
+    return AM_OK;
+}
+
+static void chunk_params(const am_matcher *h, long long &C, long long &ov) {
+    ov = llround(h->cfg.overlap_s * (double)h->sr);      // audio_matcher.rs:99
+    C = llround(h->cfg.chunk_size_s * (double)h->sr);    // audio_matcher.rs:100
+}
+
+size_t am_num_chunks(const am_matcher *h, size_t frames) {
+    if (!h) return 0;
+    long long C, ov;
+    chunk_params(h, C, ov);
+    if (C <= 0 || frames == 0) return 0;
+    return (frames + (size_t)C - 1) / (size_t)C;          // chunked(C + ov, C), audio_matcher.rs:104
+}
+
+int am_is_overshadowed(const am_peak *element, const am_peak *other, uint32_t sr, double max_distance_s) {
+    if (!element || !other) return 0;                      // None never overshadows, audio_matcher.rs:149
+    uint64_t e = start_ns(element->start, sr), b = start_ns(other->start, sr);
+    if (e < b) std::swap(e, b);
+    return ((e - b) < duration_ns(max_distance_s)) && (other->prominence > element->prominence);
+}
+
+am_status am_merge_peaks(am_peak *peaks, size_t n, uint32_t sr, double distance_s, am_peak *out, size_t cap,
+                         size_t *n_out) {
+    if (!n_out || (n && (!peaks || !out))) return fail(AM_ERR_INVALID, "NULL argument");
+    if (sr == 0) return fail(AM_ERR_INVALID, "sample rate 0");
+    // sorted_by position.start (stable, audio_matcher.rs:135); equal starts keep chunk order
+    std::stable_sort(peaks, peaks + n, [](const am_peak &a, const am_peak &b) {
+        if (a.start != b.start) return a.start < b.start;
+        if (a.snippet_id != b.snippet_id) return a.snippet_id < b.snippet_id;
+        return a.chunk < b.chunk;
+    });
+    size_t k = 0;
+    for (size_t i = 0; i < n; ++i) {                       // filter_surrounding, audio_matcher.rs:136-139
+        const am_peak *before = (i > 0 && peaks[i - 1].snippet_id == peaks[i].snippet_id) ? &peaks[i - 1] : nullptr;
+        const am_peak *after = (i + 1 < n && peaks[i + 1].snippet_id == peaks[i].snippet_id) ? &peaks[i + 1] : nullptr;
+        if (am_is_overshadowed(&peaks[i], before, sr, distance_s) || am_is_overshadowed(&peaks[i], after, sr, distance_s))
+            continue;
+        if (k < cap) out[k] = peaks[i];
+        ++k;
+    }
+    *n_out = k;
+    if (k > cap) return fail(AM_ERR_CAPACITY, "%zu peaks, capacity %zu", k, cap);
+    return AM_OK;
+}
+
+am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_first_frame, size_t buf_frames,
+                               size_t total_frames, am_sample_fmt fmt, am_mem mem, int scale, size_t first_chunk,
+                               size_t num_chunks, int final_filter, am_peak *out, size_t cap, size_t *n_out) {
+    if (!h || !n_out) return fail(AM_ERR_INVALID, "NULL argument");
+    if ((int)fmt < 0 || (int)fmt > 2) return fail(AM_ERR_INVALID, "bad sample format");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    memset(&h->stats, 0, sizeof h->stats);
+    *n_out = 0;
+    long long C, ov;
+    chunk_params(h, C, ov);
+    const long long L = (long long)total_frames, m = (long long)h->m;
+    if (C <= 0) return fail(AM_ERR_INVALID, "chunk size rounds to 0 samples");
+    if (C + ov >= (1ll << 31)) return fail(AM_ERR_UNSUPPORTED, "chunk window of %lld samples exceeds 2^31", C + ov);
+    const size_t total_chunks = am_num_chunks(h, total_frames);
+    if (first_chunk >= total_chunks || num_chunks == 0) return AM_OK;
+    num_chunks = std::min(num_chunks, total_chunks - first_chunk);
+    const long long c_first = (long long)first_chunk, c_last = c_first + (long long)num_chunks;   // [c_first, c_last)
+    // frames the range reads: [C c_first, min(L, C (c_last-1) + C + ov))
+    const long long need_lo = C * c_first, need_hi = std::min(L, C * (c_last - 1) + C + ov);
+    if (!stream || (long long)buf_first_frame > need_lo || (long long)(buf_first_frame + buf_frames) < need_hi)
+        return fail(AM_ERR_INVALID, "stream buffer [%zu, %zu) does not cover frames [%lld, %lld) of chunks [%lld, %lld)",
+                    buf_first_frame, buf_first_frame + buf_frames, need_lo, need_hi, c_first, c_last);
+
+    auto chunk_end = [&](long long i) {                      // one past the last global offset chunk i evaluates
+        long long n = std::min(C + ov, L - C * i);
+        return n >= m ? C * i + n - m + 1 : C * i;
+    };
+    unsigned long long outputs = 0;
+    for (long long i = c_last - 1; i >= c_first; --i)
+        if (chunk_end(i) > C * i) { outputs = (unsigned long long)(chunk_end(i) - C * c_first); break; }
+    if (outputs == 0) return AM_OK;                          // every window shorter than the snippet
+    int log2n;
+    TRY(choose_log2n(h, outputs, log2n));
+    const float scalar = (float)(1.0 / (double)(1ull << log2n)) * (scale ? h->inv_ac : 1.0f);
+
+    // segments of K logical chunks share one dense correlation buffer
+    const size_t seg_floats = (env_mb("AM_SEGMENT_MB", 1024) << 20) / sizeof(float);
+    long long K = std::max<long long>(1, (long long)(seg_floats / (size_t)C));
+    K = std::min<long long>(K, (long long)num_chunks);
+    const long long seg_c_len = K * C + std::max<long long>(ov - m + 1, 0) + 1;
+    TRY(h->d_c.reserve((size_t)seg_c_len));
+    const long long tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
+    TRY(h->d_tmin.reserve((size_t)(K * tiles_stride)));
+    TRY(h->d_tmax.reserve((size_t)(K * tiles_stride)));
+    const int pk_cap = h->cfg.max_peaks_per_chunk ? (int)h->cfg.max_peaks_per_chunk : 1024;
+    const size_t pk_smem = (size_t)pk_cap * (2 * sizeof(unsigned) + 4 * sizeof(float) + 1);
+    if (pk_smem > 200 * 1024) return fail(AM_ERR_INVALID, "max_peaks_per_chunk %d too large", pk_cap);
+    TRY(set_smem(amp::k_chunk_peaks, pk_smem));
+    const size_t dev_cap = std::min<size_t>((size_t)num_chunks * (size_t)pk_cap, (size_t)1 << 22);
+    TRY(h->d_peaks.reserve(dev_cap));
+    CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
+    amp::PeakOut po;
+    po.peaks = h->d_peaks.p; po.cap = dev_cap; po.count = h->d_count.p; po.flags = (unsigned *)(h->d_count.p + 1);
+    const unsigned long long min_dist = (unsigned long long)h->cfg.distance_s * (unsigned long long)h->sr;  // as_secs(), :228
+    const size_t fb = fmt_bytes(fmt);
+
+    int seg_idx = 0;
+    for (long long i0 = c_first; i0 < c_last; i0 += K, ++seg_idx) {
+        const long long i1 = std::min(c_last, i0 + K);
+        const long long g0 = C * i0;
+        long long g1 = g0;
+        for (long long i = i1 - 1; i >= i0; --i)
+            if (chunk_end(i) > C * i) { g1 = chunk_end(i); break; }
+        if (g1 <= g0) continue;
+        amk::StreamView sv;
+        sv.fmt = (int)fmt; sv.total = L; sv.lead = 0;
+        if (mem == AM_MEM_HOST) {
+            const int b = seg_idx & 1;
+            const long long f_lo = g0, f_hi = std::min(L, g1 + m - 1);
+            const size_t bytes = (size_t)(f_hi - f_lo) * fb;
+            CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // kernels that read this buffer are done
+            TRY(h->d_stage[b].reserve(bytes));
+            CU(cudaMemcpyAsync(h->d_stage[b].p, (const unsigned char *)stream + (size_t)(f_lo - (long long)buf_first_frame) * fb,
+                               bytes, cudaMemcpyHostToDevice, h->copy_stream));
+            CU(cudaEventRecord(h->ev_up[b], h->copy_stream));
+            CU(cudaStreamWaitEvent(h->stream, h->ev_up[b], 0));
+            h->stats.h2d_bytes += bytes;
+            sv.x = h->d_stage[b].p; sv.buf_first = f_lo; sv.buf_frames = f_hi - f_lo;
+        } else {
+            sv.x = stream; sv.buf_first = (long long)buf_first_frame; sv.buf_frames = (long long)buf_frames;
+        }
+        TRY(run_correlation(h, sv, g0, g1, log2n, scalar, h->d_c.p, g0));
+        if (mem == AM_MEM_HOST) CU(cudaEventRecord(h->ev_done[seg_idx & 1], h->stream));
+        amp::ChunkGeom cg;
+        cg.C = C; cg.ov = ov; cg.m = m; cg.total = L; cg.first_chunk = i0; cg.c_g0 = g0; cg.tiles_stride = (int)tiles_stride;
+        dim3 tgrid((unsigned)tiles_stride, (unsigned)(i1 - i0));
+        LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p));
+        LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<<<(unsigned)(i1 - i0), 256, pk_smem, h->stream>>>(
+                                        h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist, pk_cap, po));
+    }
+    unsigned long long cnt[2] = {0, 0};
+    CU(cudaMemcpyAsync(cnt, h->d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    prof_collect(h);
+    h->stats.d2h_bytes += sizeof cnt;
+    h->stats.frames = (uint64_t)(need_hi - need_lo);
+    h->stats.chunks = (uint32_t)num_chunks;
+    if ((unsigned)cnt[1] & 1u)
+        return fail(AM_ERR_CAPACITY, "a chunk produced more than max_peaks_per_chunk = %d peak candidates (raise it or the prominence)", pk_cap);
+    if (cnt[0] > dev_cap) return fail(AM_ERR_CAPACITY, "%llu peaks exceed the device list capacity %zu", cnt[0], dev_cap);
+    std::vector<am_peak> all((size_t)cnt[0]);
+    if (cnt[0]) {
+        CU(cudaMemcpy(all.data(), h->d_peaks.p, (size_t)cnt[0] * sizeof(am_peak), cudaMemcpyDeviceToHost));
+        h->stats.d2h_bytes += (size_t)cnt[0] * sizeof(am_peak);
+    }
+    if (!final_filter) {
+        std::stable_sort(all.begin(), all.end(), [](const am_peak &a, const am_peak &b) {
+            if (a.chunk != b.chunk) return a.chunk < b.chunk;
+            return a.height > b.height || (a.height == b.height && a.start < b.start);
+        });
+        *n_out = all.size();
+        if (all.size() > cap) return fail(AM_ERR_CAPACITY, "%zu peaks, capacity %zu", all.size(), cap);
+        if (!all.empty()) {
+            if (!out) return fail(AM_ERR_INVALID, "NULL output buffer");
+            memcpy(out, all.data(), all.size() * sizeof(am_peak));
+        }
+        return AM_OK;
+    }
+    std::vector<am_peak> kept(all.size());
+    size_t nk = 0;
+    TRY(am_merge_peaks(all.data(), all.size(), h->sr, h->cfg.distance_s, kept.data(), kept.size(), &nk));
+    *n_out = nk;
+    if (nk > cap) return fail(AM_ERR_CAPACITY, "%zu peaks, capacity %zu", nk, cap);
+    if (nk) {
+        if (!out) return fail(AM_ERR_INVALID, "NULL output buffer");
+        memcpy(out, kept.data(), nk * sizeof(am_peak));
+    }
+    return AM_OK;
+}
+
+am_status am_calc_chunks(am_matcher *h, const void *stream, size_t frames, am_sample_fmt fmt, am_mem mem, int scale,
+                         am_peak *out, size_t cap, size_t *n_out) {
+    return am_calc_chunks_range(h, stream, 0, frames, frames, fmt, mem, scale, 0, (size_t)-1, 1, out, cap, n_out);
+}
+
+am_status am_synth_pcm16_device(uint64_t seed, uint64_t first, size_t count, int16_t *dev_out, void *cuda_stream) {
+    if (count == 0) return AM_OK;
+    if (!dev_out) return fail(AM_ERR_INVALID, "NULL buffer");
+    unsigned grid = (unsigned)std::min<size_t>((count + 255) / 256, 148 * 32);
+    k_synth_pcm16<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(seed, first, count, dev_out);
+    CU(cudaGetLastError());
+    return AM_OK;
+}
+am_status am_synth_plant_device(int16_t *dev_pcm, size_t frames, int channels, const int16_t *dev_snip, size_t m,
+                                uint64_t offset, int shift, void *cuda_stream) {
+    if (m == 0) return AM_OK;
+    if (!dev_pcm || !dev_snip || (channels != 1 && channels != 2) || shift < 0 || shift > 15)
+        return fail(AM_ERR_INVALID, "bad argument");
+    k_synth_plant<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(dev_pcm, frames, channels, dev_snip, m,
+                                                                                      offset, shift);
+    CU(cudaGetLastError());
+    return AM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,353 @@
+// am_kernels.cuh -- CUDA kernels of the snippet-vs-stream matcher (sm_100a).
+//
+// Overlap-save FFT cross-correlation.  The stream is cut into blocks of N = 2^k
+// frames that advance by V_N = N - m + 1 frames; two real blocks are packed as the
+// real and imaginary part of one complex signal (correlation with a real snippet is
+// real-linear, so Re/Im of IFFT(FFT(z) conj(S)) are the two blocks' correlations).
+//
+//   N <= 2^13 : k_small   one pass, whole transform in one thread group
+//   N >  2^13 : four-step N = N1 x N2 (element n = n1*N2 + n2, spectrum bin k = k1 + N1*k2)
+//       k_col_fwd  PCM -> f32 (scale/downmix fused into the load, mp3_reader.rs:12,35),
+//                  length-N1 column transforms over a tile of T columns, twiddle, store A[k1][n2]
+//       k_row      per row k1: length-N2 transform, multiply by the conjugate snippet
+//                  spectrum, inverse transform, all in registers; in-place on A
+//       k_col_inv  conjugate twiddle, inverse column transforms, crop to the valid
+//                  outputs, scale by 1/(N sum s^2), store the correlation
+//
+// Replaces fftconvolve::fftcorrelate as called at src/matcher/audio_matcher.rs:305 and the
+// maths of MyConvolve::correlate (:414-457).
+#pragma once
+#include "am_fft.cuh"
+
+namespace amk {
+
+using amfft::EPT;
+using amfft::RegFFT;
+
+enum { FMT_F32_MONO = 0, FMT_I16_MONO = 1, FMT_I16_STEREO = 2 };
+
+// A window of the (virtual) stream resident in device memory.  Virtual frame v maps to
+// stream frame v - lead (lead = number of zeros prepended for Mode::Full / Mode::Same);
+// frames outside [0, total) read as zero; frames inside must lie in the buffer.
+struct StreamView {
+    const void *x;
+    int fmt;
+    long long buf_first;   // stream frame index of x[0]
+    long long buf_frames;  // frames held in x
+    long long total;       // stream length in frames
+    long long lead;
+};
+
+__device__ __forceinline__ float load_frame(const StreamView &s, long long v) {
+    long long f = v - s.lead;
+    if (f < 0 || f >= s.total) return 0.f;
+    f -= s.buf_first;
+    if (f < 0 || f >= s.buf_frames) return 0.f;
+    const float pcm_factor = 1.0f / 65535.0f;                   // mp3_reader.rs:12
+    if (s.fmt == FMT_F32_MONO) return __ldg((const float *)s.x + f);
+    if (s.fmt == FMT_I16_MONO) {
+        float a = (float)__ldg((const short *)s.x + f);
+        return __fmul_rn(__fmul_rn(__fadd_rn(a, a), 0.5f), pcm_factor);
+    }
+    short2 lr = __ldg((const short2 *)s.x + f);
+    return __fmul_rn(__fmul_rn(__fadd_rn((float)lr.x, (float)lr.y), 0.5f), pcm_factor);   // mp3_reader.rs:35
+}
+
+// One launch group of overlap-save blocks.
+struct BlockGroup {
+    StreamView sv;
+    long long g0;       // virtual output offset of block 0
+    long long g_end;    // outputs at or beyond g_end are dropped
+    long long VN;       // N - m + 1
+    int nblocks;        // real blocks (pairs = (nblocks + 1) / 2)
+    float *c;           // correlation out, c[g - c_g0]
+    long long c_g0;
+    float scalar;       // 1/N or 1/(N sum s^2)
+};
+
+__device__ __forceinline__ void store_pair(const BlockGroup &g, int pair, long long n, float2 val) {
+    if (n >= g.VN) return;
+    long long o = g.g0 + (long long)(2 * pair) * g.VN + n;
+    if (o < g.g_end) g.c[o - g.c_g0] = val.x * g.scalar;
+    if (2 * pair + 1 < g.nblocks) {
+        o += g.VN;
+        if (o < g.g_end) g.c[o - g.c_g0] = val.y * g.scalar;
+    }
+}
+__device__ __forceinline__ float2 load_pair(const BlockGroup &g, int pair, long long n) {
+    long long v = g.g0 + (long long)(2 * pair) * g.VN + n;
+    float re = load_frame(g.sv, v);
+    float im = (2 * pair + 1 < g.nblocks) ? load_frame(g.sv, v + g.VN) : 0.f;
+    return make_float2(re, im);
+}
+
+// ---- single-pass path -------------------------------------------------------------
+// MODE 0: correlate a block pair.  MODE 1: spectrum of the zero-padded snippet -> conj -> spec.
+template <int LOG2N> struct SmallCfg {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int GT = N / EPT;                       // threads per transform
+    static constexpr int THREADS = GT < 128 ? 128 : GT;
+    static constexpr int G = THREADS / GT;                   // transforms per CTA
+    static constexpr size_t SMEM = (size_t)G * RegFFT<LOG2N, 0, false>::SMEM_ELEMS * sizeof(float2);
+};
+
+template <int LOG2N, int MODE>
+__global__ void __launch_bounds__(SmallCfg<LOG2N>::THREADS)
+k_small(BlockGroup g, float2 *__restrict__ spec, const float2 *__restrict__ tw) {
+    typedef RegFFT<LOG2N, 0, false> F;
+    typedef RegFFT<LOG2N, 0, true> I;
+    typedef SmallCfg<LOG2N> Cfg;
+    extern __shared__ float2 sm_all[];
+    const int grp = threadIdx.x / Cfg::GT, gtid = threadIdx.x % Cfg::GT;
+    float2 *sm = sm_all + (size_t)grp * F::SMEM_ELEMS;
+    const int npairs = (g.nblocks + 1) / 2;
+    int pair = blockIdx.x * Cfg::G + grp;
+    const bool active = pair < npairs;
+    if (!active) pair = npairs - 1;                          // keep every thread in the barriers
+
+    float2 v[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int idx, t;
+        F::template in_coord<0>(gtid, j, idx, t);
+        v[j] = load_pair(g, pair, idx);
+    }
+    F::run(v, sm, gtid, tw);
+    if constexpr (MODE == 1) {
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                int idx, t;
+                F::out_coord(gtid, j, idx, t);
+                spec[idx] = make_float2(v[j].x, -v[j].y);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int idx, t;
+        F::out_coord(gtid, j, idx, t);
+        v[j] = amfft::cmul(v[j], __ldg(&spec[idx]));
+    }
+    __syncthreads();                                         // exchange buffer is reused by the inverse
+    I::run(v, sm, gtid, tw);
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            int idx, t;
+            I::out_coord(gtid, j, idx, t);
+            store_pair(g, pair, idx, v[j]);
+        }
+    }
+}
+
+// ---- four-step path ---------------------------------------------------------------
+template <int L1> struct ColCfg {
+    static constexpr int LT = (L1 >= 11) ? 3 : (L1 >= 7 ? 4 : 11 - L1);   // tile columns: N1*T >= 2048, <= 128 KB
+    static constexpr int T = 1 << LT;
+    static constexpr int THREADS = ((1 << L1) * T) / EPT;
+    static constexpr size_t SMEM = (size_t)RegFFT<L1, LT, false>::SMEM_ELEMS * sizeof(float2);
+};
+
+// exp(-+ 2 pi i p / N), p < N <= 2^24 (p and 2/N exact in fp32)
+__device__ __forceinline__ float2 twiddle_big(unsigned p, float two_over_n, bool inverse) {
+    float s, c;
+    sincospif((float)p * two_over_n, &s, &c);
+    return make_float2(c, inverse ? s : -s);
+}
+
+// grid (N2 / T, pairs).  A[pair][k1][n2] = W_N^{n2 k1} * sum_{n1} z[n1 N2 + n2] W_N1^{n1 k1}
+template <int L1>
+__global__ void __launch_bounds__(ColCfg<L1>::THREADS)
+k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__restrict__ tw) {
+    typedef ColCfg<L1> Cfg;
+    typedef RegFFT<L1, Cfg::LT, false> F;
+    extern __shared__ float2 sm_all[];
+    const int tid = threadIdx.x, pair = blockIdx.y;
+    const int n2_0 = blockIdx.x << Cfg::LT;
+    float2 v[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int idx, t;
+        F::template in_coord<0>(tid, j, idx, t);
+        v[j] = load_pair(g, pair, ((long long)idx << log2n2) + n2_0 + t);
+    }
+    F::run(v, sm_all, tid, tw);
+    const float two_over_n = 2.0f / (float)(1u << (L1 + log2n2));
+    float2 *Ap = A + ((size_t)pair << (L1 + log2n2));
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int k1, t;
+        F::out_coord(tid, j, k1, t);
+        int n2 = n2_0 + t;
+        float2 w = twiddle_big((unsigned)n2 * (unsigned)k1, two_over_n, false);
+        Ap[((size_t)k1 << log2n2) + n2] = amfft::cmul(v[j], w);
+    }
+}
+
+// grid (N2 / T, pairs).  y[n1 N2 + n2] = sum_{k1} W_N1^{-n1 k1} W_N^{-n2 k1} B[k1][n2]
+template <int L1>
+__global__ void __launch_bounds__(ColCfg<L1>::THREADS)
+k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *__restrict__ tw) {
+    typedef ColCfg<L1> Cfg;
+    typedef RegFFT<L1, Cfg::LT, true> I;
+    extern __shared__ float2 sm_all[];
+    const int tid = threadIdx.x, pair = blockIdx.y;
+    const int n2_0 = blockIdx.x << Cfg::LT;
+    const float two_over_n = 2.0f / (float)(1u << (L1 + log2n2));
+    const float2 *Ap = A + ((size_t)pair << (L1 + log2n2));
+    float2 v[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int k1, t;
+        I::template in_coord<0>(tid, j, k1, t);
+        int n2 = n2_0 + t;
+        float2 w = twiddle_big((unsigned)n2 * (unsigned)k1, two_over_n, true);
+        v[j] = amfft::cmul(Ap[((size_t)k1 << log2n2) + n2], w);
+    }
+    I::run(v, sm_all, tid, tw);
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int n1, t;
+        I::out_coord(tid, j, n1, t);
+        store_pair(g, pair, ((long long)n1 << log2n2) + n2_0 + t, v[j]);
+    }
+}
+
+template <int L2> struct RowCfg {
+    static constexpr int N = 1 << L2;
+    static constexpr int GT = N / EPT;
+    static constexpr int THREADS = GT < 128 ? 128 : GT;
+    static constexpr int G = THREADS / GT;
+    static constexpr size_t SMEM = (size_t)G * RegFFT<L2, 0, false>::SMEM_ELEMS * sizeof(float2);
+};
+
+// rows = pairs * N1.  MODE 0: A[row] <- IFFT(FFT(A[row]) * spec[k1]) in place.
+// MODE 1: spec[row] <- conj(FFT(A[row]))  (snippet spectrum, one "pair").
+template <int L2, int MODE>
+__global__ void __launch_bounds__(RowCfg<L2>::THREADS)
+k_row(float2 *__restrict__ A, float2 *__restrict__ spec, int log2n1, int rows, const float2 *__restrict__ tw) {
+    typedef RegFFT<L2, 0, false> F;
+    typedef RegFFT<L2, 0, true> I;
+    typedef RowCfg<L2> Cfg;
+    extern __shared__ float2 sm_all[];
+    const int grp = threadIdx.x / Cfg::GT, gtid = threadIdx.x % Cfg::GT;
+    float2 *sm = sm_all + (size_t)grp * F::SMEM_ELEMS;
+    int row = blockIdx.x * Cfg::G + grp;
+    const bool active = row < rows;
+    if (!active) row = rows - 1;
+    float2 *Ar = A + ((size_t)row << L2);
+    float2 v[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int idx, t;
+        F::template in_coord<0>(gtid, j, idx, t);
+        v[j] = Ar[idx];
+    }
+    F::run(v, sm, gtid, tw);
+    const int k1 = row & ((1 << log2n1) - 1);
+    float2 *Sr = spec + ((size_t)k1 << L2);
+    if constexpr (MODE == 1) {
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                int idx, t;
+                F::out_coord(gtid, j, idx, t);
+                Sr[idx] = make_float2(v[j].x, -v[j].y);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int idx, t;
+        F::out_coord(gtid, j, idx, t);
+        v[j] = amfft::cmul(v[j], __ldg(&Sr[idx]));
+    }
+    __syncthreads();
+    I::run(v, sm, gtid, tw);
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            int idx, t;
+            I::out_coord(gtid, j, idx, t);
+            Ar[idx] = v[j];
+        }
+    }
+}
+
+// sum of squares of the snippet in double (inverse_sample_auto_correlation, audio_matcher.rs:321-329)
+__global__ void k_sumsq(StreamView sv, long long m, double *out) {
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x) {
+        double s = (double)load_frame(sv, i);
+        acc += s * s;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) atomicAdd(out, acc);
+    }
+}
+
+// materialise a window of the stream as f32 (only used to hand the caller's PCM snippet back)
+__global__ void k_to_f32(StreamView sv, long long first, long long count, float *out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < count) out[i] = load_frame(sv, first + i);
+}
+
+// ---- snippet spectrum in double precision ----------------------------------------------
+// Runs once per matcher and block length, so the conjugate snippet spectrum the hot kernels
+// multiply with is correctly rounded fp32 instead of carrying an fp32 transform's error.
+// Plain Stockham radix-2 passes in global memory (ping-pong), natural-order output.
+__global__ void k_spec64_load(StreamView sv, long long n, double2 *out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2((double)load_frame(sv, i), 0.0);
+}
+__global__ void k_spec64_pass(const double2 *__restrict__ in, double2 *__restrict__ out, long long half, long long ns) {
+    long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= half) return;
+    long long k = j & (ns - 1);
+    double s, c;
+    sincospi(-(double)k / (double)ns, &s, &c);          // exp(-2 pi i k / (2 ns))
+    double2 a = in[j], b = in[j + half];
+    double2 bw = make_double2(b.x * c - b.y * s, b.x * s + b.y * c);
+    long long o = ((j - k) << 1) + k;
+    out[o] = make_double2(a.x + bw.x, a.y + bw.y);
+    out[o + ns] = make_double2(a.x - bw.x, a.y - bw.y);
+}
+// spec[(k & (N1-1)) * N2 + (k >> log2n1)] = conj(X[k])   (four-step layout; log2n1 = 0: natural)
+__global__ void k_spec64_store(const double2 *__restrict__ X, long long n, int log2n1, int log2n2, float2 *spec) {
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    long long pos = ((k & ((1ll << log2n1) - 1)) << log2n2) + (k >> log2n1);
+    double2 x = X[k];
+    spec[pos] = make_float2((float)x.x, (float)(-x.y));
+}
+
+// ---- direct form for very short snippets -------------------------------------------------
+// m <= DIRECT_MAX_M: c[g] = scalar * sum_j x[g + j] s[j], one output per thread, snippet in
+// shared memory.  Cheaper than block transforms at this size and exact to fp32 rounding.
+constexpr int DIRECT_MAX_M = 64;
+__global__ void __launch_bounds__(256)
+k_direct(StreamView sv, const float *__restrict__ snip, int m, long long g0, long long g1, float *c, long long c_g0,
+         float scalar) {
+    __shared__ float s_sn[DIRECT_MAX_M];
+    __shared__ float s_x[256 + DIRECT_MAX_M];
+    const long long base = g0 + (long long)blockIdx.x * 256;
+    if (threadIdx.x < m) s_sn[threadIdx.x] = snip[threadIdx.x];
+    for (int i = threadIdx.x; i < 256 + m - 1; i += 256) s_x[i] = load_frame(sv, base + i);
+    __syncthreads();
+    const long long g = base + threadIdx.x;
+    if (g >= g1) return;
+    float acc = 0.f;
+    for (int j = 0; j < m; ++j) acc = fmaf(s_x[threadIdx.x + j], s_sn[j], acc);
+    c[g - c_g0] = acc * scalar;
+}
+
+}  // namespace amk

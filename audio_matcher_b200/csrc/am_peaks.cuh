@@ -1,0 +1,324 @@
+// am_peaks.cuh -- per-logical-chunk peak extraction on the device.
+//
+// Restates what calc_chunks does with each chunk's correlation
+// (src/matcher/audio_matcher.rs:124 -> find_peaks :221-230 -> find_peaks::PeakFinder):
+// local maxima (plateau aware, endpoints excluded), prominence >= min_prominence,
+// greedy min-distance suppression in descending height order.  The chunk geometry
+// (window C + ov stepped by C, V = n - m + 1 outputs, audio_matcher.rs:99-104,119)
+// scopes the prominence walks, so it is reproduced here index for index.
+//
+//   k_tile_minmax   min / max of every 1024-sample tile of every chunk
+//   k_chunk_peaks   one CTA per chunk: chunk minimum -> exact-safe candidate filter
+//                   (prominence <= height - chunk_min) -> warp-cooperative prominence
+//                   walks that skip whole tiles through the min/max summaries ->
+//                   min-distance suppression (block argmax loop) -> append to the output
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace amp {
+
+constexpr int TP_LOG2 = 10;
+constexpr int TP = 1 << TP_LOG2;       // samples per summary tile
+
+struct DevPeak {                        // mirrors am_peak (include/audio_matcher.h)
+    unsigned long long start, end;
+    float height, prominence, left_diff, right_diff;
+    unsigned snippet_id, chunk;
+};
+
+struct ChunkGeom {
+    long long C, ov, m;                 // samples
+    long long total;                    // virtual stream length (with lead/tail padding)
+    long long first_chunk;              // global index of the segment's first chunk
+    long long c_g0;                     // global offset of c[0]
+    int tiles_stride;                   // tiles allocated per chunk in tmin/tmax
+};
+
+__device__ __forceinline__ long long chunk_valid_len(const ChunkGeom &g, long long chunk) {
+    long long off = g.C * chunk;
+    if (off >= g.total) return 0;
+    long long n = g.total - off;
+    if (n > g.C + g.ov) n = g.C + g.ov;
+    return n >= g.m ? n - g.m + 1 : 0;
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// grid (tiles_stride, chunks in segment), 256 threads
+__global__ void __launch_bounds__(256)
+k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin, float *__restrict__ tmax) {
+    const long long chunk = g.first_chunk + blockIdx.y;
+    const long long V = chunk_valid_len(g, chunk);
+    const long long k0 = (long long)blockIdx.x << TP_LOG2;
+    if (k0 >= V) return;
+    const float *y = c + (g.C * chunk - g.c_g0);
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < TP / 256; ++i) {
+        long long k = k0 + i * 256 + threadIdx.x;
+        if (k < V) {
+            float v = __ldg(y + k);
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    __shared__ float smn[8], smx[8];
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+        size_t o = (size_t)blockIdx.y * g.tiles_stride + blockIdx.x;
+        tmin[o] = mn;
+        tmax[o] = mx;
+    }
+}
+
+// Walk from the peak towards lower (DIR = -1) or higher (DIR = +1) indices until a sample
+// strictly greater than h; returns the minimum of the samples passed (h if none).  The whole
+// warp calls this with identical arguments.  [lo, hi) is the range still to scan.
+template <int DIR>
+__device__ float walk_min(const float *__restrict__ y, long long V, const float *__restrict__ tmin,
+                          const float *__restrict__ tmax, long long from, float h) {
+    const int lane = threadIdx.x & 31;
+    float m = h;
+    bool found = false;
+    // raw scan of [a, b): towards DIR, 32 samples per step; stops at the first sample > h
+    auto raw = [&](long long a, long long b) {
+        long long done = 0, len = b - a;
+        while (done < len && !found) {
+            long long k = (DIR < 0) ? (b - 1 - done - lane) : (a + done + lane);
+            bool valid = (DIR < 0) ? (k >= a) : (k < b);
+            float v = valid ? __ldg(y + k) : CUDART_INF_F;
+            unsigned hi = __ballot_sync(0xffffffffu, valid && v > h);
+            if (hi) {
+                int first = __ffs(hi) - 1;
+                m = fminf(m, warp_min(lane < first ? v : CUDART_INF_F));
+                found = true;
+            } else {
+                m = fminf(m, warp_min(v));
+                done += 32;
+            }
+        }
+    };
+    const long long ntiles = (V + TP - 1) >> TP_LOG2;
+    if (DIR < 0) {
+        // samples [0, from) remain; first the part inside from's own tile
+        long long t = from >> TP_LOG2;                 // tile containing index from (or == ntiles boundary)
+        long long lo = t << TP_LOG2;
+        if (from > lo) raw(lo, from);
+        long long t_hi = t;                            // tiles [0, t_hi) remain
+        while (!found && t_hi > 0) {
+            long long tt = t_hi - 1 - lane;
+            bool valid = tt >= 0;
+            float mx = valid ? tmax[tt] : -CUDART_INF_F, mn = valid ? tmin[tt] : CUDART_INF_F;
+            unsigned hi = __ballot_sync(0xffffffffu, valid && mx > h);
+            if (hi) {
+                int first = __ffs(hi) - 1;
+                m = fminf(m, warp_min(lane < first ? mn : CUDART_INF_F));
+                long long te = t_hi - 1 - first;
+                raw(te << TP_LOG2, (te + 1) << TP_LOG2);
+            } else {
+                m = fminf(m, warp_min(mn));
+                t_hi -= 32;
+            }
+        }
+    } else {
+        // samples [from, V) remain
+        long long t = from >> TP_LOG2;
+        long long hi_end = (t + 1) << TP_LOG2;
+        if (hi_end > V) hi_end = V;
+        if (from < hi_end) raw(from, hi_end);
+        long long t_lo = t + 1;                        // tiles [t_lo, ntiles) remain
+        while (!found && t_lo < ntiles) {
+            long long tt = t_lo + lane;
+            bool valid = tt < ntiles;
+            float mx = valid ? tmax[tt] : -CUDART_INF_F, mn = valid ? tmin[tt] : CUDART_INF_F;
+            unsigned hi = __ballot_sync(0xffffffffu, valid && mx > h);
+            if (hi) {
+                int first = __ffs(hi) - 1;
+                m = fminf(m, warp_min(lane < first ? mn : CUDART_INF_F));
+                long long te = t_lo + first;
+                long long e = (te + 1) << TP_LOG2;
+                if (e > V) e = V;
+                raw(te << TP_LOG2, e);
+            } else {
+                m = fminf(m, warp_min(mn));
+                t_lo += 32;
+            }
+        }
+    }
+    return m;
+}
+
+struct PeakOut {
+    DevPeak *peaks;                 // global output list
+    unsigned long long cap;
+    unsigned long long *count;      // appended entries (may exceed cap: overflow is detected by the host)
+    unsigned *flags;                // bit 0: per-chunk candidate list overflow
+};
+
+// dynamic shared memory: pk_cap * (2*u32 + 4*f32 + u8)
+// grid = chunks in segment, 256 threads
+__global__ void __launch_bounds__(256)
+k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict__ tmin_all,
+              const float *__restrict__ tmax_all, float min_prom, unsigned long long min_dist, int pk_cap,
+              PeakOut out) {
+    extern __shared__ unsigned char smraw[];
+    unsigned *p_start = (unsigned *)smraw;
+    unsigned *p_end = p_start + pk_cap;
+    float *p_h = (float *)(p_end + pk_cap);
+    float *p_prom = p_h + pk_cap;
+    float *p_ld = p_prom + pk_cap;
+    float *p_rd = p_ld + pk_cap;
+    unsigned char *p_alive = (unsigned char *)(p_rd + pk_cap);
+    __shared__ float s_red[8];
+    __shared__ int s_redi[8];
+    __shared__ int s_ncand, s_win;
+    __shared__ float s_cmin;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long chunk = g.first_chunk + blockIdx.x;
+    const long long V = chunk_valid_len(g, chunk);
+    if (V < 3) return;                                              // endpoints are never peaks
+    const float *y = c + (g.C * chunk - g.c_g0);
+    const float *tmin = tmin_all + (size_t)blockIdx.x * g.tiles_stride;
+    const float *tmax = tmax_all + (size_t)blockIdx.x * g.tiles_stride;
+    const long long ntiles = (V + TP - 1) >> TP_LOG2;
+
+    // (a) chunk minimum
+    float mn = CUDART_INF_F;
+    for (long long t = tid; t < ntiles; t += 256) mn = fminf(mn, tmin[t]);
+    mn = warp_min(mn);
+    if (lane == 0) s_red[warp] = mn;
+    if (tid == 0) s_ncand = 0;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) mn = fminf(mn, s_red[w]);
+        s_cmin = mn;
+    }
+    __syncthreads();
+    const float cmin = s_cmin;
+
+    // (b) candidates: local maxima whose upper bound h - chunk_min on the prominence passes.
+    // prominence = h - max(lmin, rmin) <= h - chunk_min (fp subtraction is monotone), so no
+    // peak that find_peaks would keep is dropped here.
+    for (long long t = warp; t < ntiles; t += 8) {
+        if (!(tmax[t] - cmin >= min_prom)) continue;                // warp-uniform
+        long long k0 = t << TP_LOG2;
+        for (int it = 0; it < TP / 32; ++it) {
+            long long k = k0 + it * 32 + lane;
+            if (k >= 1 && k < V - 1) {
+                float yk = __ldg(y + k);
+                if (__ldg(y + k - 1) < yk && yk - cmin >= min_prom) {
+                    long long a = k + 1;
+                    while (a < V - 1 && __ldg(y + a) == yk) ++a;    // plateau
+                    if (__ldg(y + a) < yk) {
+                        int slot = atomicAdd(&s_ncand, 1);
+                        if (slot < pk_cap) {
+                            p_start[slot] = (unsigned)k;
+                            p_end[slot] = (unsigned)a;
+                            p_h[slot] = yk;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    int ncand = s_ncand;
+    if (ncand > pk_cap) {
+        if (tid == 0) atomicOr(out.flags, 1u);
+        ncand = pk_cap;
+    }
+
+    // (c) exact prominence, one warp per candidate
+    for (int i = warp; i < ncand; i += 8) {
+        const float h = p_h[i];
+        const long long s = p_start[i], e = p_end[i];
+        float lmin = walk_min<-1>(y, V, tmin, tmax, s, h);
+        float rmin = walk_min<+1>(y, V, tmin, tmax, e, h);
+        if (lane == 0) {
+            float prom = h - fmaxf(lmin, rmin);
+            p_prom[i] = prom;
+            p_ld[i] = h - __ldg(y + s - 1);
+            p_rd[i] = h - __ldg(y + e);
+            p_alive[i] = prom >= min_prom;                          // with_min_prominence, :227
+        }
+    }
+    __syncthreads();
+
+    auto emit = [&](int i) {
+        unsigned long long slot = atomicAdd(out.count, 1ull);
+        if (slot < out.cap) {
+            DevPeak p;
+            const unsigned long long off = (unsigned long long)(g.C * chunk);   // offset_range, lib.rs:8-10
+            p.start = off + p_start[i];
+            p.end = off + p_end[i];
+            p.height = p_h[i];
+            p.prominence = p_prom[i];
+            p.left_diff = p_ld[i];
+            p.right_diff = p_rd[i];
+            p.snippet_id = 0;
+            p.chunk = (unsigned)chunk;
+            out.peaks[slot] = p;
+        }
+    };
+
+    // (d) with_min_distance (:228): greedy in descending height, ties by lower position
+    if (min_dist == 0) {
+        for (int i = tid; i < ncand; i += 256)
+            if (p_alive[i]) emit(i);
+        return;
+    }
+    for (;;) {
+        float bh = -CUDART_INF_F;
+        int bi = -1;
+        for (int i = tid; i < ncand; i += 256) {
+            if (p_alive[i]) {
+                float h = p_h[i];
+                if (bi < 0 || h > bh || (h == bh && p_start[i] < p_start[bi])) { bh = h; bi = i; }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            float oh = __shfl_xor_sync(0xffffffffu, bh, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || oh > bh || (oh == bh && p_start[oi] < p_start[bi]))) { bh = oh; bi = oi; }
+        }
+        if (lane == 0) { s_red[warp] = bh; s_redi[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 8; ++w) {
+                float oh = s_red[w];
+                int oi = s_redi[w];
+                if (oi >= 0 && (bi < 0 || oh > bh || (oh == bh && p_start[oi] < p_start[bi]))) { bh = oh; bi = oi; }
+            }
+            s_win = bi;
+            if (bi >= 0) emit(bi);
+        }
+        __syncthreads();
+        const int win = s_win;
+        if (win < 0) break;
+        const unsigned long long mw = ((unsigned long long)p_start[win] + p_end[win]) / 2;
+        for (int i = tid; i < ncand; i += 256) {
+            if (p_alive[i]) {
+                unsigned long long mi = ((unsigned long long)p_start[i] + p_end[i]) / 2;
+                unsigned long long d = mi > mw ? mi - mw : mw - mi;
+                if (i == win || d < min_dist) p_alive[i] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace amp

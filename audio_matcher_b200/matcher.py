@@ -1,0 +1,302 @@
+"""Host-side mirror of the reference's matcher interface over the CUDA library.
+
+Same names, argument meaning and error behaviour as src/matcher/audio_matcher.rs:
+  Mode (:54-59), Config / PeakConfig (:24-53), trait CorrelateAlgo (:65-76) implemented by
+  CudaConvolve (the drop-in for LibConvolve :282-344), calc_chunks (:88-141),
+  is_overshadowed (:143-160), test_data (:481-483).
+All numeric work happens in libaudio_matcher_b200.so; nothing here computes a correlation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from enum import IntEnum
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+
+class Mode(IntEnum):                      # audio_matcher.rs:54-59
+    Full = N.MODE_FULL
+    Same = N.MODE_SAME
+    Valid = N.MODE_VALID
+
+
+@dataclass
+class PeakConfig:                         # audio_matcher.rs:31-35
+    distance: float = 8 * 60.0            # seconds (args.rs:75)
+    prominence: float = 0.13              # already /100 (audio_matcher.rs:44)
+
+
+@dataclass
+class Config:                             # audio_matcher.rs:24-30 (the progress-bar arrow is UI only)
+    chunk_size: float = 60.0              # seconds (args.rs:71)
+    overlap_length: float = -1.0          # seconds; < 0 => snippet duration m / sr (audio_matcher.rs:41)
+    peak_config: PeakConfig = field(default_factory=PeakConfig)
+    fft_log2: int = 0                     # extension: overlap-save block length override
+    max_peaks_per_chunk: int = 0
+
+    @classmethod
+    def from_args(cls, prominence_percent: float = 13.0, distance: float | None = None,
+                  chunk_size: float | None = None, s_duration: float = -1.0) -> "Config":
+        """Config::from_args (audio_matcher.rs:38-52) with the CLI defaults of args.rs:70-76."""
+        return cls(chunk_size=60.0 if chunk_size is None else chunk_size, overlap_length=s_duration,
+                   peak_config=PeakConfig(distance=480.0 if distance is None else distance,
+                                          prominence=prominence_percent / 100.0))
+
+    def _native(self) -> N.AmConfig:
+        return N.AmConfig(self.chunk_size, self.overlap_length, self.peak_config.distance,
+                          self.peak_config.prominence, self.fft_log2, self.max_peaks_per_chunk, 0)
+
+
+@dataclass
+class Peak:                               # find_peaks::Peak<f32>
+    position: range
+    height: float
+    prominence: float
+    left_diff: float
+    right_diff: float
+    chunk: int = 0
+    snippet_id: int = 0
+
+    @property
+    def start(self) -> int:
+        return self.position.start
+
+    def _native(self) -> N.AmPeak:
+        return N.AmPeak(self.position.start, self.position.stop, self.height, self.prominence, self.left_diff,
+                        self.right_diff, self.snippet_id, self.chunk)
+
+    @classmethod
+    def _from_native(cls, p: N.AmPeak) -> "Peak":
+        return cls(range(p.start, p.end), p.height, p.prominence, p.left_diff, p.right_diff, p.chunk, p.snippet_id)
+
+
+def test_data(rng: Iterable[int]) -> np.ndarray:
+    """audio_matcher.rs:481-483: integer range -> Vec<f32>."""
+    return np.fromiter((float(i) for i in rng), dtype=np.float32)
+
+
+def _describe(samples):
+    """-> (pointer, frames, fmt, mem, keepalive).  Accepts numpy f32 / int16 arrays (mono 1-D or
+    stereo (frames, 2)) in host memory and CUDA tensors of the same dtypes/shapes in device memory."""
+    if hasattr(samples, "is_cuda") and hasattr(samples, "data_ptr"):           # torch tensor
+        t = samples if samples.is_contiguous() else samples.contiguous()
+        name = str(t.dtype)
+        if name.endswith("float32"):
+            kind = "f32"
+        elif name.endswith("int16"):
+            kind = "i16"
+        else:
+            raise TypeError(f"unsupported tensor dtype {t.dtype}")
+        shape = tuple(t.shape)
+        mem = N.MEM_DEVICE if t.is_cuda else N.MEM_HOST
+        ptr = t.data_ptr()
+        keep = t
+    else:
+        a = np.asarray(samples)
+        if a.dtype == np.int16:
+            kind = "i16"
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            kind = "f32"
+        a = np.ascontiguousarray(a)
+        shape, mem, ptr, keep = a.shape, N.MEM_HOST, a.ctypes.data, a
+    if len(shape) == 1:
+        fmt = N.FMT_F32_MONO if kind == "f32" else N.FMT_I16_MONO
+    elif len(shape) == 2 and shape[1] == 2 and kind == "i16":
+        fmt = N.FMT_I16_STEREO                                                  # "can only handle stereo", mp3_reader.rs:26
+    elif len(shape) == 2 and shape[1] == 1:
+        fmt = N.FMT_F32_MONO if kind == "f32" else N.FMT_I16_MONO
+    else:
+        raise TypeError(f"unsupported sample layout {shape} / {kind}")
+    return ptr, int(shape[0]), fmt, mem, keep
+
+
+class CudaConvolve:
+    """CorrelateAlgo<f32> (audio_matcher.rs:65-76) backed by the CUDA library: the drop-in for
+    LibConvolve::new(sample_data) (audio_matcher.rs:289)."""
+
+    def __init__(self, sample_data, sr: int = 48000, config: Config | None = None, stream: int | None = None):
+        ptr, frames, fmt, mem, keep = _describe(sample_data)
+        if mem != N.MEM_HOST:
+            raise TypeError("the snippet is taken from host memory (LibConvolve::new owns a copy)")
+        if frames == 0:
+            raise ValueError("empty snippet")
+        self.sr = int(sr)
+        self.m = frames
+        self._config = config or Config()
+        cfg = self._config._native()
+        h = C.c_void_p()
+        if fmt == N.FMT_F32_MONO:
+            N.check(N.lib().am_matcher_create(ptr, frames, self.sr, C.byref(cfg), C.byref(h)))
+        else:
+            N.check(N.lib().am_matcher_create_pcm16(ptr, frames, 2 if fmt == N.FMT_I16_STEREO else 1, self.sr,
+                                                    C.byref(cfg), C.byref(h)))
+        self._h = h
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            N.lib().am_matcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int) -> None:
+        N.check(N.lib().am_matcher_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_config(self, config: Config) -> None:
+        self._config = config
+        cfg = config._native()
+        N.check(N.lib().am_matcher_set_config(self._h, C.byref(cfg)))
+
+    def stats(self) -> dict:
+        s = N.AmStats()
+        N.check(N.lib().am_matcher_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in N.AmStats._fields_}
+
+    def set_profiling(self, on: bool) -> None:
+        N.check(N.lib().am_matcher_set_profiling(self._h, int(on)))
+
+    def kernel_times(self) -> dict:
+        buf = (N.AmKernelTime * 16)()
+        got = C.c_size_t()
+        N.check(N.lib().am_matcher_get_kernel_times(self._h, buf, 16, C.byref(got)))
+        return {buf[i].name.decode(): {"launches": buf[i].launches, "total_ms": buf[i].total_ms} for i in range(got.value)}
+
+    # --- trait CorrelateAlgo -------------------------------------------------------------
+    def inverse_sample_auto_correlation(self) -> float:
+        out = C.c_float()
+        N.check(N.lib().am_inverse_sample_auto_correlation(self._h, C.byref(out)))
+        return out.value
+
+    def correlate_with_sample(self, within, mode: Mode = Mode.Valid, scale: bool = False) -> np.ndarray:
+        ptr, n, fmt, mem, keep = _describe(within)
+        olen = N.lib().am_out_len(n, self.m, int(mode))
+        out = np.empty(olen, dtype=np.float32)
+        got = C.c_size_t()
+        N.check(N.lib().am_correlate(self._h, ptr, n, fmt, mem, int(mode), int(bool(scale)), out.ctypes.data, olen,
+                                     N.MEM_HOST, C.byref(got)))
+        return out[:got.value]
+
+    def scale(self, data: np.ndarray) -> None:
+        """CorrelateAlgo::scale (audio_matcher.rs:73-75): in-place multiply by the inverse autocorrelation."""
+        data *= np.float32(self.inverse_sample_auto_correlation())
+
+    # --- calc_chunks plumbing ---------------------------------------------------------------
+    def num_chunks(self, frames: int) -> int:
+        return N.lib().am_num_chunks(self._h, frames)
+
+    def _calc(self, samples, scale: bool, total_frames: int | None, buf_first_frame: int, first_chunk: int,
+              num_chunks: int | None, final_filter: bool, cap: int) -> list[Peak]:
+        ptr, frames, fmt, mem, keep = _describe(samples)
+        total = frames if total_frames is None else int(total_frames)
+        buf = (N.AmPeak * cap)()
+        got = C.c_size_t()
+        nc = (1 << 62) if num_chunks is None else int(num_chunks)
+        N.check(N.lib().am_calc_chunks_range(self._h, ptr, buf_first_frame, frames, total, fmt, mem, int(bool(scale)),
+                                             first_chunk, nc, int(final_filter), buf, cap, C.byref(got)))
+        return [Peak._from_native(buf[i]) for i in range(got.value)]
+
+
+def calc_chunks(sr: int, m_samples, algo_with_sample: CudaConvolve, scale: bool, config: Config,
+                cap: int = 1 << 16) -> list[Peak]:
+    """calc_chunks (audio_matcher.rs:88-141).  `m_samples` is the decoded stream (numpy array in host
+    memory or CUDA tensor in device memory; f32 mono, int16 mono, or int16 stereo (frames, 2))."""
+    if int(sr) != algo_with_sample.sr:
+        raise ValueError(f"sample rate mismatch {algo_with_sample.sr} != {sr}")       # CliError::SampleRateMismatch
+    algo_with_sample.set_config(config)
+    return algo_with_sample._calc(m_samples, scale, None, 0, 0, None, True, cap)
+
+
+def is_overshadowed(element: Peak, other: Peak | None, sr: int, max_distance: float) -> bool:
+    """audio_matcher.rs:143-160."""
+    if other is None:
+        return False
+    e, o = element._native(), other._native()
+    return bool(N.lib().am_is_overshadowed(C.byref(e), C.byref(o), sr, max_distance))
+
+
+def merge_peaks(peaks: Sequence[Peak], sr: int, distance: float) -> list[Peak]:
+    """Global stable sort by start + filter_surrounding (audio_matcher.rs:135-139) over peaks gathered
+    from several shards."""
+    n = len(peaks)
+    src = (N.AmPeak * max(n, 1))(*[p._native() for p in peaks])
+    dst = (N.AmPeak * max(n, 1))()
+    got = C.c_size_t()
+    N.check(N.lib().am_merge_peaks(src, n, sr, distance, dst, n, C.byref(got)))
+    return [Peak._from_native(dst[i]) for i in range(got.value)]
+
+
+def shard_chunks(total_chunks: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous chunk range [first, first + count) of rank `rank`."""
+    first = rank * total_chunks // world_size
+    last = (rank + 1) * total_chunks // world_size
+    return first, last - first
+
+
+def shard_frames(first_chunk: int, num_chunks: int, total_frames: int, sr: int, config: Config, m: int) -> tuple[int, int]:
+    """Frames [lo, hi) a rank must hold for its chunk range: its chunks plus the overlap halo."""
+    C_ = int(round(config.chunk_size * sr))
+    ov = int(round((config.overlap_length if config.overlap_length >= 0 else m / sr) * sr))
+    lo = C_ * first_chunk
+    hi = min(total_frames, C_ * (first_chunk + num_chunks - 1) + C_ + ov) if num_chunks > 0 else lo
+    return lo, hi
+
+
+def gather_peaks(local: Sequence[Peak], group=None) -> list[Peak]:
+    """All-gather of the per-rank candidate lists (KB-sized) through torch.distributed (NCCL on
+    GPUs, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return list(local)
+    ws = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    rows = np.zeros((len(local), 4), dtype=np.int64)
+    for i, p in enumerate(local):
+        f = np.array([p.height, p.prominence, p.left_diff, p.right_diff], dtype=np.float32).view(np.int32).astype(np.int64)
+        rows[i, 0] = p.position.start
+        rows[i, 1] = p.position.stop
+        rows[i, 2] = (f[0] & 0xFFFFFFFF) | ((f[1] & 0xFFFFFFFF) << 32)
+        rows[i, 3] = (f[2] & 0xFFFFFFFF) | ((f[3] & 0xFFFFFFFF) << 32)
+    chunk_ids = np.array([p.chunk for p in local], dtype=np.int64)
+    count = torch.tensor([len(local)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(count) for _ in range(ws)]
+    dist.all_gather(counts, count, group=group)
+    mx = max(int(c.item()) for c in counts)
+    payload = torch.zeros((max(mx, 1), 5), dtype=torch.int64, device=dev)
+    if len(local):
+        payload[:len(local), :4] = torch.from_numpy(rows).to(dev)
+        payload[:len(local), 4] = torch.from_numpy(chunk_ids).to(dev)
+    gathered = [torch.zeros_like(payload) for _ in range(ws)]
+    dist.all_gather(gathered, payload, group=group)
+    out: list[Peak] = []
+    for r in range(ws):
+        g = gathered[r][:int(counts[r].item())].cpu().numpy()
+        for row in g:
+            f = np.array([row[2] & 0xFFFFFFFF, (row[2] >> 32) & 0xFFFFFFFF, row[3] & 0xFFFFFFFF,
+                          (row[3] >> 32) & 0xFFFFFFFF], dtype=np.uint32).view(np.float32)
+            out.append(Peak(range(int(row[0]), int(row[1])), float(f[0]), float(f[1]), float(f[2]), float(f[3]),
+                            int(row[4])))
+    return out
+
+
+def calc_chunks_sharded(sr: int, shard_samples, algo_with_sample: CudaConvolve, scale: bool, config: Config, *,
+                        total_frames: int, buf_first_frame: int, first_chunk: int, num_chunks: int, group=None,
+                        cap: int = 1 << 16) -> list[Peak]:
+    """Multi-GPU calc_chunks: this rank runs logical chunks [first_chunk, first_chunk + num_chunks) on
+    the frames it holds (its range plus the overlap halo, no halo exchange), the per-rank candidates
+    are all-gathered, and every rank applies the global sort + neighbour filter."""
+    algo_with_sample.set_config(config)
+    local = algo_with_sample._calc(shard_samples, scale, total_frames, buf_first_frame, first_chunk, num_chunks,
+                                   False, cap)
+    return merge_peaks(gather_peaks(local, group), sr, config.peak_config.distance)

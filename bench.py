@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- audio-hours matched per second (snippet vs stream), BASELINE.json's metric.
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
+  python bench.py --impl reference --gpus N ...            the reference algorithm's CPU path (oracle port)
+
+A step is one calc_chunks pass over the whole workload (default: BASELINE.json configs[1], one 10 s
+snippet vs a 24 h 48 kHz mono int16 stream per GPU, overlap-save block 2^22).  With N > 1 every rank
+matches its own 24 h shard of an N*24 h stream (weak scaling; chunk ranges + halo, no data-path
+collective) and only the peak candidates are all-gathered over NCCL.  `value` is timed with CUDA events
+with the PCM already in HBM; `e2e` is the same call with the PCM in pinned host memory (H2D inside the
+timed region) and the peak list read back.  One JSON line on stdout from rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (sr, channels, snippet_s, stream_hours per GPU, fft_log2)   -- BASELINE.json configs
+    "cfg1": (44100, 1, 10.0, 1.0, 22),
+    "cfg2": (48000, 1, 10.0, 24.0, 22),
+    "cfg4": (44100, 1, 30.0, 125.0, 23),
+    "cfg5": (96000, 2, 2.0, 12.5, 20),
+}
+METRIC = "audio-hours matched/sec (snippet vs stream)"
+UNIT = "audio-hours/s"
+CHUNK_S, DIST_S, PROM = 60.0, 480.0, 0.13
+PLANT_PERIOD_S, PLANT_JITTER_S = 600.0, 30.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def plant_plan(sr, snippet_s, total_frames):
+    """(offset, shift) of every planted occurrence in the global stream."""
+    from oracle import am_oracle as orc
+    m, P, J, C = int(round(snippet_s * sr)), int(round(PLANT_PERIOD_S * sr)), int(round(PLANT_JITTER_S * sr)), int(round(CHUNK_S * sr))
+    out, k = [], 0
+    while k * P + m <= total_frames or k in (3, 4):
+        o = orc.plant_offset(k, P, J, C)
+        if o + m <= total_frames:
+            out.append((o, k % 4))
+        k += 1
+        if k > 10_000_000:
+            break
+    return out
+
+
+def run_reference(args, wl):
+    """The reference algorithm's own CPU path (exact-length complex FFTs per 60 s chunk, snippet FFT
+    recomputed per chunk, one worker thread per core), via the oracle port -- the Rust crate cannot be
+    built in this image.  Each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import am_oracle as orc
+    sr, ch, snip_s, hours, fft_log2 = wl
+    cores = min(os.cpu_count() or 1, orc.threads(), 32)
+    chunks = cores if args.sample_chunks <= 0 else args.sample_chunks
+    stream_s = chunks * CHUNK_S
+    pcm, snip, _ = orc.synth_case(sr, stream_s + snip_s, snip_s, channels=ch, chunk_s=CHUNK_S,
+                                  plant_period_s=PLANT_PERIOD_S, plant_jitter_s=PLANT_JITTER_S)
+    x, s = orc.pcm16_to_f32(pcm, ch), orc.pcm16_to_f32(snip, 1)
+    cfg = orc.make_config(CHUNK_S, len(s) / sr, DIST_S, PROM)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        peaks = orc.calc_chunks(x, s, sr, cfg, scale=True, precision=32, threads=cores, n_chunks=chunks)
+        dt = time.perf_counter() - t
+        if i >= args.warmup:
+            times.append(dt)
+        log(f"[reference] step {i}: {dt:.2f}s, {len(peaks)} peaks")
+    total = sum(times)
+    value = (stream_s / 3600.0) * len(times) / total
+    sample = f"{chunks} logical chunks ({stream_s:.0f} s of {sr} Hz audio) of the {args.workload} workload per step, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args, wl), "note": "oracle port of the reference CPU path; Rust crate not buildable here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_name(args, wl):
+    sr, ch, snip_s, hours, fft_log2 = wl
+    return (f"{args.workload}: one {snip_s:g} s snippet vs {hours:g} h {sr} Hz {'stereo' if ch == 2 else 'mono'} int16 "
+            f"stream per GPU, chunk 60 s, distance 480 s, prominence 0.13")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--hours", type=float, default=0.0, help="override stream hours per GPU")
+    ap.add_argument("--fft-log2", type=int, default=0)
+    ap.add_argument("--sample-chunks", type=int, default=0, help="CPU baseline sample size in logical chunks")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = list(WORKLOADS[args.workload])
+    if args.hours > 0:
+        wl[3] = args.hours
+    if args.fft_log2:
+        wl[4] = args.fft_log2
+    wl = tuple(wl)
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import audio_matcher_b200 as am
+    from audio_matcher_b200 import _native as N
+    from audio_matcher_b200.matcher import shard_chunks, shard_frames, gather_peaks, merge_peaks
+    from oracle import am_oracle as orc   # workload constants + CPU baseline only
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sr, ch, snip_s, hours, fft_log2 = wl
+    m = int(round(snip_s * sr))
+    frames_per_gpu = int(round(hours * 3600 * sr))
+    total_frames = frames_per_gpu * world
+    conf = am.Config(chunk_size=CHUNK_S, overlap_length=-1.0, peak_config=am.PeakConfig(DIST_S, PROM), fft_log2=fft_log2)
+    snip_np = orc.synth_pcm16(orc.SEED_SNIP, 0, m)
+    stream = torch.cuda.current_stream()
+    algo = am.CudaConvolve(snip_np, sr=sr, config=conf, stream=stream.cuda_stream)
+    total_chunks = algo.num_chunks(total_frames)
+    c0, nc = shard_chunks(total_chunks, world, rank)
+    lo, hi = shard_frames(c0, nc, total_frames, sr, conf, m)
+
+    # ---- synthetic shard, generated on the device (identical integers to the oracle's generator)
+    L = N.lib()
+    pcm = torch.empty(((hi - lo), ch) if ch == 2 else (hi - lo,), dtype=torch.int16, device="cuda")
+    N.check(L.am_synth_pcm16_device(orc.SEED_STREAM, lo * ch, (hi - lo) * ch, pcm.data_ptr(), stream.cuda_stream))
+    snip_dev = torch.from_numpy(snip_np).cuda()
+    plan = plant_plan(sr, snip_s, total_frames)
+    expected = set()
+    for o, shift in plan:
+        if o + m <= lo or o >= hi:
+            continue
+        skip = max(0, lo - o)
+        N.check(L.am_synth_plant_device(pcm.data_ptr(), hi - lo, ch, snip_dev.data_ptr() + 2 * skip, m - skip,
+                                        o + skip - lo, shift, stream.cuda_stream))
+    expected = {o for o, _ in plan}
+    torch.cuda.synchronize()
+
+    def step(samples):
+        if world == 1:
+            return algo._calc(samples, True, total_frames, lo, c0, nc, True, 1 << 16)
+        local = algo._calc(samples, True, total_frames, lo, c0, nc, False, 1 << 16)
+        return merge_peaks(gather_peaks(local), sr, DIST_S)
+
+    def timed(samples, warmup, steps, profile=False):
+        for _ in range(warmup):
+            peaks = step(samples)
+        if profile:
+            algo.set_profiling(True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            peaks = step(samples)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, peaks
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, peaks = timed(pcm, args.warmup, args.steps, profile=True)
+    clocks = sampler.stop()
+    ktimes = algo.kernel_times()
+    algo.set_profiling(False)
+    stats = algo.stats()
+    ms_per_step = ms / args.steps
+    value = (total_frames / sr / 3600.0) / (ms_per_step / 1000.0)
+    # sanity: every reported offset is a planted one (the oracle parity proper lives in tests/)
+    starts = [p.position.start for p in peaks]
+    verified = len(starts) > 0 and all(s in expected for s in starts)
+
+    # ---- roofline of the dominant kernel (algorithmic bytes, SURVEY.md 8d / DESIGN.md)
+    n_fft = 1 << stats["fft_log2"] if stats["fft_log2"] else 0
+    b_in = 2 * ch
+    pairs = (stats["fft_blocks"] + 1) // 2
+    model_bytes = {
+        "k_col_fwd": pairs * (2 * n_fft * b_in + 8 * n_fft),
+        "k_row": pairs * 16 * n_fft,
+        "k_col_inv": pairs * 8 * n_fft,
+        "k_small": pairs * 2 * n_fft * b_in,
+    }
+    peak_gbs, peak_src = measured_hbm_peak()
+    dom = max((k for k in ktimes if k in model_bytes), key=lambda k: ktimes[k]["total_ms"], default=None)
+    roofline = None
+    if dom:
+        per_step_ms = ktimes[dom]["total_ms"] / args.steps
+        achieved = model_bytes[dom] / (per_step_ms / 1000.0) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                    "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": ktimes[dom]["launches"] / args.steps, "ms_per_step": per_step_ms,
+                    "algorithmic_bytes_per_step": model_bytes[dom]}
+    vn = n_fft - m + 1 if n_fft else 1
+    step_model_bytes = (hi - lo) * (b_in + 16) * n_fft / vn if n_fft else 0
+    kernel_share = {k: round(v["total_ms"] / args.steps, 4) for k, v in ktimes.items()}
+
+    # ---- end to end: PCM in pinned host memory, H2D inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=True)
+        host.copy_(pcm)
+        torch.cuda.synchronize()
+        e_ms, e_peaks = timed(host, min(args.warmup, 2), args.steps)
+        est = algo.stats()
+        e_value = (total_frames / sr / 3600.0) / (e_ms / args.steps / 1000.0)
+        verified = verified and [p.position.start for p in e_peaks] == starts
+        e2e = {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": est["h2d_bytes"], "d2h_bytes_per_step": est["d2h_bytes"],
+               "ms_per_step": e_ms / args.steps}
+        del host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = min(os.cpu_count() or 1, orc.threads(), 32)
+        chunks = cores if args.sample_chunks <= 0 else args.sample_chunks
+        spcm, ssnip, _ = orc.synth_case(sr, chunks * CHUNK_S + snip_s, snip_s, channels=ch, chunk_s=CHUNK_S,
+                                        plant_period_s=PLANT_PERIOD_S, plant_jitter_s=PLANT_JITTER_S)
+        x, s = orc.pcm16_to_f32(spcm, ch), orc.pcm16_to_f32(ssnip, 1)
+        t = time.perf_counter()
+        orc.calc_chunks(x, s, sr, orc.make_config(CHUNK_S, len(s) / sr, DIST_S, PROM), scale=True, precision=32,
+                        threads=cores, n_chunks=chunks)
+        dt = time.perf_counter() - t
+        cpu_baseline = {"value": (chunks * CHUNK_S / 3600.0) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{chunks} logical chunks ({chunks * CHUNK_S:.0f} s of audio) of this workload, "
+                                  f"exact-length f32 FFTs per chunk like the reference, {dt:.1f} s wall"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args, wl), "fft_log2": stats["fft_log2"],
+                   "four_step": f"{1 << stats['log2_n1']}x{1 << stats['log2_n2']}", "frames_per_gpu": hi - lo,
+                   "l2_policy": "inputs larger than L2 (PCM per GPU %.1f GB)" % ((hi - lo) * b_in / 1e9),
+                   "peaks_found": len(starts), "planted": len(plan), "verified_offsets_are_planted": verified,
+                   "model_bytes_per_step": step_model_bytes,
+                   "model_gbs": step_model_bytes / (ms_per_step / 1000.0) / 1e9,
+                   "model_frac_of_hbm": step_model_bytes / (ms_per_step / 1000.0) / 1e9 / peak_gbs,
+                   "kernel_ms_per_step": kernel_share},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": stats["kernel_launches"] * args.steps,
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,177 @@
+/* audio_matcher.h -- C ABI of libaudio_matcher_b200.so
+ *
+ * B200-native (sm_100a) drop-in for the one data-parallel hot path of
+ * NilsJochem/audio-matcher: slide a snippet over a long stream with block-wise
+ * FFT cross-correlation and pick the peak offsets.  The reference has no FFI of
+ * its own; the seams these entry points replace are (paths relative to the
+ * reference checkout):
+ *
+ *   LibConvolve::new                              src/matcher/audio_matcher.rs:289
+ *   CorrelateAlgo::inverse_sample_auto_correlation  src/matcher/audio_matcher.rs:66,321-329
+ *   CorrelateAlgo::correlate_with_sample          src/matcher/audio_matcher.rs:67-72,331-343
+ *   calc_chunks                                   src/matcher/audio_matcher.rs:88-141
+ *   Config / PeakConfig                           src/matcher/audio_matcher.rs:24-53
+ *   find_peaks::Peak<f32>                         src/matcher/audio_matcher.rs:97,124-127
+ *   PCM scale + stereo downmix                    src/matcher/mp3_reader.rs:12,33-36
+ *
+ * INTEGRATION.md shows the Rust binding (`extern "C"` block + CudaConvolve shim)
+ * a maintainer of the reference would add.
+ *
+ * Conventions: every call returns an am_status; am_last_error() returns a
+ * thread-local message for the last failure on the calling thread.  Handles are
+ * opaque and internally locked (a handle may be shared between threads, calls on
+ * it serialise).  All output buffers are caller-allocated: capacity in, count
+ * out.  No C++ types, no exceptions, no torch types cross this boundary.
+ * There is NO CPU fallback: without a CUDA device every compute entry point
+ * fails with AM_ERR_CUDA.
+ */
+#ifndef AUDIO_MATCHER_B200_H
+#define AUDIO_MATCHER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AM_ABI_VERSION 1
+
+typedef enum {
+    AM_OK = 0,
+    AM_ERR_INVALID = 1,     /* bad argument */
+    AM_ERR_CUDA = 2,        /* CUDA runtime / launch failure, or no device */
+    AM_ERR_CAPACITY = 3,    /* caller buffer or an internal per-chunk peak list too small */
+    AM_ERR_NOMEM = 4,
+    AM_ERR_UNSUPPORTED = 5  /* e.g. snippet longer than the largest FFT block */
+} am_status;
+
+/* Mode, src/matcher/audio_matcher.rs:54-59 */
+typedef enum { AM_MODE_FULL = 0, AM_MODE_SAME = 1, AM_MODE_VALID = 2 } am_mode;
+
+/* stream / snippet sample formats.  I16 variants apply the reference's scale
+ * (l + r) * 0.5 * (1/65535) on load (mono: l = r = s), mp3_reader.rs:12,35 */
+typedef enum { AM_FMT_F32_MONO = 0, AM_FMT_I16_MONO = 1, AM_FMT_I16_STEREO = 2 } am_sample_fmt;
+
+typedef enum { AM_MEM_HOST = 0, AM_MEM_DEVICE = 1 } am_mem;
+
+/* Config + PeakConfig (audio_matcher.rs:24-53) as plain data */
+typedef struct {
+    double chunk_size_s;   /* args.rs:71, default 60 */
+    double overlap_s;      /* snippet duration (audio_matcher.rs:41); < 0 => m / sr */
+    double distance_s;     /* args.rs:75, default 480; find_peaks uses whole seconds (:228) */
+    float prominence;      /* already divided by 100 (audio_matcher.rs:44), default 0.13 */
+    uint32_t fft_log2;     /* overlap-save block length 2^fft_log2; 0 = choose from the snippet length */
+    uint32_t max_peaks_per_chunk;  /* capacity of the per-chunk list before min-distance suppression; 0 = 1024 */
+    uint32_t reserved;
+} am_config;
+
+/* find_peaks::Peak<f32> with global positions (after offset_range, lib.rs:8-10) */
+typedef struct {
+    uint64_t start, end;   /* position: Range<usize>, end exclusive */
+    float height;
+    float prominence;
+    float left_diff, right_diff;
+    uint32_t snippet_id;   /* always 0 for a single-snippet matcher */
+    uint32_t chunk;        /* logical chunk index that produced the peak */
+} am_peak;
+
+/* counters of the work the last am_correlate / am_calc_chunks* call did */
+typedef struct {
+    uint64_t kernel_launches;   /* CUDA kernels launched by this library */
+    uint64_t fft_blocks;        /* overlap-save blocks transformed */
+    uint64_t frames;            /* stream frames covered */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t fft_log2, log2_n1, log2_n2;   /* block length and its four-step split (n1 = 1 => single pass) */
+    uint32_t chunks;
+} am_stats;
+
+/* kernel classes for the optional per-kernel device timing */
+enum {
+    AM_K_COL_FWD = 0, AM_K_ROW = 1, AM_K_COL_INV = 2, AM_K_SMALL = 3, AM_K_DIRECT = 4, AM_K_TILE_MINMAX = 5,
+    AM_K_CHUNK_PEAKS = 6, AM_K_SPECTRUM = 7, AM_KERNEL_CLASSES = 8
+};
+typedef struct {
+    int kernel_class;
+    uint64_t launches;
+    double total_ms;       /* sum of cudaEvent-bracketed launch durations on the matcher's stream */
+    char name[24];
+} am_kernel_time;
+
+typedef struct am_matcher am_matcher;
+
+const char *am_last_error(void);
+int am_abi_version(void);
+/* number of visible CUDA devices (0 without a driver); never fails */
+int am_device_count(void);
+
+void am_config_default(am_config *cfg);
+
+/* LibConvolve::new (audio_matcher.rs:289): takes a copy of the snippet, uploads it to the
+ * CURRENT CUDA device, computes sum(s^2) and the conjugate snippet spectrum once. */
+am_status am_matcher_create(const float *snippet, size_t m, uint32_t sr, const am_config *cfg, am_matcher **out);
+/* same from 16-bit PCM (channels 1 or 2), scaled/downmixed like mp3_reader.rs:35 */
+am_status am_matcher_create_pcm16(const int16_t *pcm, size_t frames, int channels, uint32_t sr,
+                                  const am_config *cfg, am_matcher **out);
+void am_matcher_destroy(am_matcher *h);
+
+/* run this matcher's work on a caller-owned cudaStream_t (NULL = the legacy default stream) */
+am_status am_matcher_set_stream(am_matcher *h, void *cuda_stream);
+am_status am_matcher_set_config(am_matcher *h, const am_config *cfg);
+am_status am_matcher_get_stats(const am_matcher *h, am_stats *out);
+/* on != 0: bracket every kernel launch with cudaEvents on the matcher's stream and accumulate
+ * per-class totals (reset by this call); read them with am_matcher_get_kernel_times */
+am_status am_matcher_set_profiling(am_matcher *h, int on);
+am_status am_matcher_get_kernel_times(const am_matcher *h, am_kernel_time *out, size_t cap, size_t *n_out);
+
+/* CorrelateAlgo::inverse_sample_auto_correlation (audio_matcher.rs:66,321-329): 1 / sum(s^2) */
+am_status am_inverse_sample_auto_correlation(am_matcher *h, float *out);
+
+/* output length of a correlation of n stream samples with m snippet samples */
+size_t am_out_len(size_t n, size_t m, am_mode mode);
+
+/* CorrelateAlgo::correlate_with_sample (audio_matcher.rs:67-72): writes the correlation
+ * (scaled by 1/sum(s^2) when scale != 0, audio_matcher.rs:73-75,306-308) to `out`.
+ * `within` and `out` live in within_mem / out_mem. */
+am_status am_correlate(am_matcher *h, const void *within, size_t n, am_sample_fmt fmt, am_mem within_mem,
+                       am_mode mode, int scale, float *out, size_t cap, am_mem out_mem, size_t *out_len);
+
+/* number of logical chunks calc_chunks makes of a stream (audio_matcher.rs:99-104) */
+size_t am_num_chunks(const am_matcher *h, size_t frames);
+
+/* calc_chunks (audio_matcher.rs:88-141): the fused path -- correlation, per-chunk peak
+ * finding (min prominence, min distance), global sort and neighbour filter.  Peaks come
+ * back sorted by start. */
+am_status am_calc_chunks(am_matcher *h, const void *stream, size_t frames, am_sample_fmt fmt, am_mem mem,
+                         int scale, am_peak *out, size_t cap, size_t *n_out);
+
+/* Shard entry point: logical chunks [first_chunk, first_chunk + num_chunks) of a stream of
+ * total_frames frames.  `stream` holds frames [buf_first_frame, buf_first_frame + buf_frames)
+ * of that stream (frames outside the buffer but inside the stream are an error if a chunk
+ * needs them).  final_filter == 0 returns the per-chunk peaks before the global sort and
+ * neighbour filter (audio_matcher.rs:132-139) so that shards can be merged with am_merge_peaks. */
+am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_first_frame, size_t buf_frames,
+                               size_t total_frames, am_sample_fmt fmt, am_mem mem, int scale,
+                               size_t first_chunk, size_t num_chunks, int final_filter,
+                               am_peak *out, size_t cap, size_t *n_out);
+
+/* global stable sort by start + filter_surrounding/is_overshadowed (audio_matcher.rs:135-160)
+ * over peaks gathered from all shards; host-only, `peaks` is reordered in place. */
+am_status am_merge_peaks(am_peak *peaks, size_t n, uint32_t sr, double distance_s, am_peak *out, size_t cap,
+                         size_t *n_out);
+
+/* is_overshadowed (audio_matcher.rs:143-160); other == NULL is None */
+int am_is_overshadowed(const am_peak *element, const am_peak *other, uint32_t sr, double max_distance_s);
+
+/* ---- synthetic workload generator (bench/test utility) -------------------
+ * Device-side, integer-only, bit-identical to the oracle's generator.
+ * out[i] = int16((hash64(seed, first + i) >> 50) - 8192) */
+am_status am_synth_pcm16_device(uint64_t seed, uint64_t first, size_t count, int16_t *dev_out, void *cuda_stream);
+/* x[(offset + j)*channels + c] = sat16((x >> 1) + (snip[j] >> shift)), j < m, frame < frames */
+am_status am_synth_plant_device(int16_t *dev_pcm, size_t frames, int channels, const int16_t *dev_snip, size_t m,
+                                uint64_t offset, int shift, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIO_MATCHER_B200_H */

@@ -38,19 +38,38 @@ struct StreamView {
     long long lead;
 };
 
+// exact int16 -> fp32 on the integer/FMA pipes (I2F.S16 runs on the slow conversion unit)
+__device__ __forceinline__ float s16_to_f32(int s) { return __int_as_float(0x4B400000 + s) - 12582912.0f; }
+// the reference's scale / downmix, mp3_reader.rs:12,35: (l + r) * 0.5 * (1/65535), mono: l = r
+__device__ __forceinline__ float pcm_scale(float l, float r) {
+    return __fmul_rn(__fmul_rn(__fadd_rn(l, r), 0.5f), 1.0f / 65535.0f);
+}
+template <int FMT> __device__ __forceinline__ float load_raw(const void *x, long long f) {
+    if (FMT == FMT_F32_MONO) return __ldg((const float *)x + f);
+    if (FMT == FMT_I16_MONO) {
+        float a = s16_to_f32((int)__ldg((const short *)x + f));
+        return pcm_scale(a, a);
+    }
+    short2 lr = __ldg((const short2 *)x + f);
+    return pcm_scale(s16_to_f32((int)lr.x), s16_to_f32((int)lr.y));
+}
+
 __device__ __forceinline__ float load_frame(const StreamView &s, long long v) {
     long long f = v - s.lead;
     if (f < 0 || f >= s.total) return 0.f;
     f -= s.buf_first;
     if (f < 0 || f >= s.buf_frames) return 0.f;
-    const float pcm_factor = 1.0f / 65535.0f;                   // mp3_reader.rs:12
-    if (s.fmt == FMT_F32_MONO) return __ldg((const float *)s.x + f);
-    if (s.fmt == FMT_I16_MONO) {
-        float a = (float)__ldg((const short *)s.x + f);
-        return __fmul_rn(__fmul_rn(__fadd_rn(a, a), 0.5f), pcm_factor);
-    }
-    short2 lr = __ldg((const short2 *)s.x + f);
-    return __fmul_rn(__fmul_rn(__fadd_rn((float)lr.x, (float)lr.y), 0.5f), pcm_factor);   // mp3_reader.rs:35
+    if (s.fmt == FMT_F32_MONO) return load_raw<FMT_F32_MONO>(s.x, f);
+    if (s.fmt == FMT_I16_MONO) return load_raw<FMT_I16_MONO>(s.x, f);
+    return load_raw<FMT_I16_STEREO>(s.x, f);
+}
+// true when both blocks of `pair` lie entirely inside the resident buffer (CTA-uniform):
+// the loads then need no per-element range checks
+__device__ __forceinline__ bool pair_in_range(const StreamView &s, long long v0, long long VN, long long n, bool two) {
+    long long lo = v0 - s.lead, hi = v0 + (two ? VN : 0) + n - s.lead;
+    long long lim = s.buf_first + s.buf_frames;
+    if (lim > s.total) lim = s.total;
+    return two && lo >= s.buf_first && hi <= lim;
 }
 
 // One launch group of overlap-save blocks.
@@ -147,6 +166,7 @@ template <int L1> struct ColCfg {
     static constexpr int LT = (L1 >= 11) ? 3 : (L1 >= 7 ? 4 : 11 - L1);   // tile columns: N1*T >= 2048, <= 128 KB
     static constexpr int T = 1 << LT;
     static constexpr int THREADS = ((1 << L1) * T) / EPT;
+    static constexpr int MINB = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : 1024 / THREADS);   // <= 64 registers
     static constexpr size_t SMEM = (size_t)RegFFT<L1, LT, false>::SMEM_ELEMS * sizeof(float2);
 };
 
@@ -157,9 +177,38 @@ __device__ __forceinline__ float2 twiddle_big(unsigned p, float two_over_n, bool
     return make_float2(c, inverse ? s : -s);
 }
 
+// v[s] *= base * step^s, s < R (product tree of depth log2 R)
+template <int R> __device__ __forceinline__ void twiddle_geo(float2 *v, float2 base, float2 step) {
+    using amfft::cmul;
+    float2 w[R];
+    w[0] = base;
+    if (R >= 2) w[1] = cmul(base, step);
+    float2 sp = step;
+#pragma unroll
+    for (int h = 2; h < R; h <<= 1) {
+        sp = cmul(sp, sp);                         // step^h
+#pragma unroll
+        for (int i = 0; i < h; ++i) w[h + i] = cmul(w[i], sp);
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) v[i] = cmul(v[i], w[i]);
+}
+
+template <int FMT, class F, int LT>
+__device__ __forceinline__ void load_tile_fast(float2 (&v)[EPT], const BlockGroup &g, long long v0, int log2n2, int n2_0, int tid) {
+    const long long f0 = v0 - g.sv.lead - g.sv.buf_first;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        int idx, t;
+        F::template in_coord<0>(tid, j, idx, t);
+        long long f = f0 + ((long long)idx << log2n2) + n2_0 + t;
+        v[j] = make_float2(load_raw<FMT>(g.sv.x, f), load_raw<FMT>(g.sv.x, f + g.VN));
+    }
+}
+
 // grid (N2 / T, pairs).  A[pair][k1][n2] = W_N^{n2 k1} * sum_{n1} z[n1 N2 + n2] W_N1^{n1 k1}
 template <int L1>
-__global__ void __launch_bounds__(ColCfg<L1>::THREADS)
+__global__ void __launch_bounds__(ColCfg<L1>::THREADS, ColCfg<L1>::MINB)
 k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__restrict__ tw) {
     typedef ColCfg<L1> Cfg;
     typedef RegFFT<L1, Cfg::LT, false> F;
@@ -167,28 +216,39 @@ k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__rest
     const int tid = threadIdx.x, pair = blockIdx.y;
     const int n2_0 = blockIdx.x << Cfg::LT;
     float2 v[EPT];
+    const long long v0 = g.g0 + (long long)(2 * pair) * g.VN;
+    if (pair_in_range(g.sv, v0, g.VN, 1ll << (L1 + log2n2), 2 * pair + 1 < g.nblocks)) {
+        if (g.sv.fmt == FMT_I16_MONO) load_tile_fast<FMT_I16_MONO, F, Cfg::LT>(v, g, v0, log2n2, n2_0, tid);
+        else if (g.sv.fmt == FMT_I16_STEREO) load_tile_fast<FMT_I16_STEREO, F, Cfg::LT>(v, g, v0, log2n2, n2_0, tid);
+        else load_tile_fast<FMT_F32_MONO, F, Cfg::LT>(v, g, v0, log2n2, n2_0, tid);
+    } else {
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        int idx, t;
-        F::template in_coord<0>(tid, j, idx, t);
-        v[j] = load_pair(g, pair, ((long long)idx << log2n2) + n2_0 + t);
+        for (int j = 0; j < EPT; ++j) {
+            int idx, t;
+            F::template in_coord<0>(tid, j, idx, t);
+            v[j] = load_pair(g, pair, ((long long)idx << log2n2) + n2_0 + t);
+        }
     }
     F::run(v, sm_all, tid, tw);
     const float two_over_n = 2.0f / (float)(1u << (L1 + log2n2));
     float2 *Ap = A + ((size_t)pair << (L1 + log2n2));
+    constexpr int RB = F::bits_at(F::NST - 1), R = 1 << RB, NB = EPT / R;
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        int k1, t;
-        F::out_coord(tid, j, k1, t);
-        int n2 = n2_0 + t;
-        float2 w = twiddle_big((unsigned)n2 * (unsigned)k1, two_over_n, false);
-        Ap[((size_t)k1 << log2n2) + n2] = amfft::cmul(v[j], w);
+    for (int l = 0; l < NB; ++l) {
+        const int id = tid + l * F::GT;
+        const int t = id & (Cfg::T - 1), q = id >> Cfg::LT;
+        const unsigned n2 = n2_0 + t;
+        // k1 = q + s (N1 / R): W_N^{n2 k1} = W_N^{n2 q} (W_N^{n2 N1 / R})^s
+        twiddle_geo<R>(&v[l * R], twiddle_big(n2 * (unsigned)q, two_over_n, false),
+                       twiddle_big(n2 << (L1 - RB), two_over_n, false));
+#pragma unroll
+        for (int s = 0; s < R; ++s) Ap[((size_t)(q + s * ((1 << L1) >> RB)) << log2n2) + n2] = v[l * R + s];
     }
 }
 
 // grid (N2 / T, pairs).  y[n1 N2 + n2] = sum_{k1} W_N1^{-n1 k1} W_N^{-n2 k1} B[k1][n2]
 template <int L1>
-__global__ void __launch_bounds__(ColCfg<L1>::THREADS)
+__global__ void __launch_bounds__(ColCfg<L1>::THREADS, ColCfg<L1>::MINB)
 k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *__restrict__ tw) {
     typedef ColCfg<L1> Cfg;
     typedef RegFFT<L1, Cfg::LT, true> I;
@@ -198,13 +258,16 @@ k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *
     const float two_over_n = 2.0f / (float)(1u << (L1 + log2n2));
     const float2 *Ap = A + ((size_t)pair << (L1 + log2n2));
     float2 v[EPT];
+    constexpr int RB = I::bits_at(0), R = 1 << RB, NB = EPT / R;
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        int k1, t;
-        I::template in_coord<0>(tid, j, k1, t);
-        int n2 = n2_0 + t;
-        float2 w = twiddle_big((unsigned)n2 * (unsigned)k1, two_over_n, true);
-        v[j] = amfft::cmul(Ap[((size_t)k1 << log2n2) + n2], w);
+    for (int l = 0; l < NB; ++l) {
+        const int id = tid + l * I::GT;
+        const int t = id & (Cfg::T - 1), q = id >> Cfg::LT;
+        const unsigned n2 = n2_0 + t;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[l * R + r] = Ap[((size_t)(q + r * ((1 << L1) >> RB)) << log2n2) + n2];
+        twiddle_geo<R>(&v[l * R], twiddle_big(n2 * (unsigned)q, two_over_n, true),
+                       twiddle_big(n2 << (L1 - RB), two_over_n, true));
     }
     I::run(v, sm_all, tid, tw);
 #pragma unroll
@@ -220,13 +283,14 @@ template <int L2> struct RowCfg {
     static constexpr int GT = N / EPT;
     static constexpr int THREADS = GT < 128 ? 128 : GT;
     static constexpr int G = THREADS / GT;
+    static constexpr int MINB = THREADS >= 512 ? 2 : 1024 / THREADS;
     static constexpr size_t SMEM = (size_t)G * RegFFT<L2, 0, false>::SMEM_ELEMS * sizeof(float2);
 };
 
 // rows = pairs * N1.  MODE 0: A[row] <- IFFT(FFT(A[row]) * spec[k1]) in place.
 // MODE 1: spec[row] <- conj(FFT(A[row]))  (snippet spectrum, one "pair").
 template <int L2, int MODE>
-__global__ void __launch_bounds__(RowCfg<L2>::THREADS)
+__global__ void __launch_bounds__(RowCfg<L2>::THREADS, RowCfg<L2>::MINB)
 k_row(float2 *__restrict__ A, float2 *__restrict__ spec, int log2n1, int rows, const float2 *__restrict__ tw) {
     typedef RegFFT<L2, 0, false> F;
     typedef RegFFT<L2, 0, true> I;

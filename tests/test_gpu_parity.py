@@ -1,0 +1,296 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs, against the committed golden vectors, and -- at BASELINE.json's full sizes --
+through size-independent properties.  Offsets must be bit-exact; scores within 1e-4 relative (fp32)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL_TOL = 1e-4          # north_star: correlation scores within 1e-4 relative in fp32
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(float(np.abs(b).max()), 1e-30))
+
+
+def test_reference_kats_on_gpu(am):
+    with open(os.path.join(GOLD, "reference_kats.json")) as f:
+        kats = json.load(f)
+    k = kats["correlate_valid"]                                            # audio_matcher.rs:489-517
+    for no_direct in ("", "1"):                                            # direct path and FFT path
+        os.environ["AM_NO_DIRECT"] = no_direct
+        if not no_direct:
+            os.environ.pop("AM_NO_DIRECT")
+        algo = am.CudaConvolve(np.array(k["sample"], np.float32), sr=1)
+        got = algo.correlate_with_sample(am.test_data(range(*k["within_range"])), am.Mode.Valid, False)
+        assert np.abs(got - np.array(k["expect"])).max() < k["abs_tol"]
+        assert abs(algo.inverse_sample_auto_correlation() - 1 / 14) < 1e-8
+        algo.close()
+    os.environ.pop("AM_NO_DIRECT", None)
+    b = kats["bench_shapes"]                                               # benches/my_benchmark.rs:29-79
+    algo = am.CudaConvolve(am.test_data(range(*b["sample_range"])), sr=1)
+    c = algo.correlate_with_sample(am.test_data(range(*b["within_range"])), am.Mode.Valid, False)
+    assert c.size == b["valid_len"] and abs(c[0] / b["first_value"] - 1) < 1e-6
+    assert abs(1 / algo.inverse_sample_auto_correlation() / b["sum_squares"] - 1) < 1e-6
+    algo.close()
+
+
+def test_find_peaks_kat_through_calc_chunks(am, orc):
+    """audio_matcher.rs:167-185 pushed through the whole device path: a 1-tap snippet makes the
+    correlation equal to the stream, one chunk covers it."""
+    y = np.array([0, 0.7, 0.5, 1.0, 0.5, 0.8, 0.0], np.float32)
+    conf = am.Config(chunk_size=7.0, overlap_length=0.0, peak_config=am.PeakConfig(0.0, 0.0))
+    algo = am.CudaConvolve(np.ones(1, np.float32), sr=1, config=conf)
+    got = am.calc_chunks(1, y, algo, True, conf)
+    algo.close()
+    assert [p.position.start for p in got] == [1, 3, 5]                    # calc_chunks sorts by start
+    assert np.allclose([p.prominence for p in got], [0.2, 1.0, 0.3], atol=1e-6)
+    assert np.allclose([p.height for p in got], [0.7, 1.0, 0.8], atol=1e-7)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("n,m,log2", [(4000, 50, 0), (4000, 50, 9), (20000, 777, 0), (25810, 4096, 14), (99538, 16384, 16),
+                                      (1574098, 262144, 20), (6292690, 480000, 22)])
+def test_correlate_vs_oracle(am, orc, n, m, log2, mode):
+    rng = np.random.default_rng(n + m)
+    w, s = rng.standard_normal(n).astype(np.float32), rng.standard_normal(m).astype(np.float32)
+    if log2 == 9:
+        os.environ["AM_NO_DIRECT"] = "1"
+    try:
+        algo = am.CudaConvolve(s, sr=1000, config=am.Config(fft_log2=log2))
+        got = algo.correlate_with_sample(w, am.Mode(mode), False)
+        st = algo.stats()
+        algo.close()
+    finally:
+        os.environ.pop("AM_NO_DIRECT", None)
+    if n * m <= 4e6:
+        ref = orc.correlate(w, s, mode, 0)
+    else:
+        from scipy import signal
+        ref = signal.correlate(w.astype(np.float64), s.astype(np.float64), mode=["full", "same", "valid"][mode], method="fft")
+    assert got.shape == ref.shape and st["kernel_launches"] > 0
+    assert _rel(got, ref) < 5e-6
+
+
+def test_correlate_formats_and_scale(am, orc):
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-32768, 32767, size=(30000, 2), dtype=np.int16)
+    snip = rng.integers(-20000, 20000, size=900, dtype=np.int16)
+    x, s = orc.pcm16_to_f32(pcm, 2), orc.pcm16_to_f32(snip, 1)
+    ref = orc.correlate(x, s, orc.MODE_VALID, 0) * orc.inv_autocorr(s, exact=True)
+    a_pcm = am.CudaConvolve(snip, sr=8000)
+    a_f32 = am.CudaConvolve(s, sr=8000)
+    got_pcm = a_pcm.correlate_with_sample(pcm, am.Mode.Valid, True)        # int16 stereo, downmix fused into the load
+    got_f32 = a_f32.correlate_with_sample(x, am.Mode.Valid, True)
+    assert np.array_equal(got_pcm, got_f32)                                # identical samples after the fused conversion
+    assert _rel(got_pcm, ref) < 5e-6
+    unscaled = a_f32.correlate_with_sample(x, am.Mode.Valid, False)
+    a_f32.scale(unscaled)                                                  # CorrelateAlgo::scale, :73-75
+    assert _rel(unscaled, ref) < 5e-6
+    import torch
+    got_dev = a_pcm.correlate_with_sample(torch.from_numpy(pcm).cuda(), am.Mode.Valid, True)
+    assert np.array_equal(got_dev, got_pcm)
+    a_pcm.close(); a_f32.close()
+
+
+def _run_case(am, orc, c, device=False, fft_log2=0):
+    pcm, snip, _ = orc.synth_case(c["sr"], c["stream_s"], c["snippet_s"], channels=c["channels"], chunk_s=c["chunk_s"],
+                                  plant_period_s=c["chunk_s"] * 2.5, plant_jitter_s=c["chunk_s"] / 2)
+    assert int(pcm.astype(np.int64).sum()) == c["pcm_checksum"]
+    conf = am.Config(chunk_size=c["chunk_s"], overlap_length=-1.0 if c["overlap_s"] is None else c["overlap_s"],
+                     peak_config=am.PeakConfig(c["distance_s"], c["prominence"]), fft_log2=fft_log2)
+    algo = am.CudaConvolve(snip, sr=c["sr"], config=conf)
+    stream = pcm.reshape(-1, 2) if c["channels"] == 2 else pcm
+    if device:
+        import torch
+        stream = torch.from_numpy(stream).cuda()
+    got = am.calc_chunks(c["sr"], stream, algo, True, conf)
+    algo.close()
+    return got
+
+
+def _assert_peaks(got, ref_rows):
+    assert [p.position.start for p in got] == [r[0] for r in ref_rows]     # bit-exact offsets after suppression
+    assert [p.position.stop for p in got] == [r[1] for r in ref_rows]
+    for p, r in zip(got, ref_rows):
+        assert abs(p.height - r[2]) <= REL_TOL * abs(r[2])
+        assert abs(p.prominence - r[3]) <= REL_TOL * abs(r[3])
+        assert p.chunk == r[4]
+
+
+@pytest.mark.parametrize("device", [False, True])
+def test_golden_cases(am, orc, device):
+    with open(os.path.join(GOLD, "oracle_cases.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        _assert_peaks(_run_case(am, orc, c, device=device), c["peaks"])
+
+
+@pytest.mark.parametrize("fft_log2", [13, 14, 17])
+def test_golden_case_other_block_lengths(am, orc, fft_log2):
+    with open(os.path.join(GOLD, "oracle_cases.json")) as f:
+        c = json.load(f)[0]
+    _assert_peaks(_run_case(am, orc, c, fft_log2=fft_log2), c["peaks"])
+
+
+@pytest.mark.parametrize("seed,dist,prom,maxpk", [(1, 0.0, 0.09, 8000), (2, 1.0, 0.09, 8000), (3, 3.0, 0.11, 0), (4, 480.0, 0.13, 0)])
+def test_calc_chunks_random_vs_oracle(am, orc, seed, dist, prom, maxpk):
+    sr = 8000
+    pcm = orc.synth_pcm16(1000 + seed, 0, sr * 33 + 17 * seed)             # ragged tail window
+    snip = orc.synth_pcm16(2000 + seed, 0, 3000 + 100 * seed)
+    for k, o in enumerate([5000, 70001, 140000, 199999]):
+        orc.synth_plant(pcm, 1, snip, o, k % 3)
+    x, s = orc.pcm16_to_f32(pcm), orc.pcm16_to_f32(snip)
+    ref = orc.calc_chunks(x, s, sr, orc.make_config(5.0, len(s) / sr, dist, prom), scale=True, precision=64, cap=1 << 18)
+    conf = am.Config(chunk_size=5.0, peak_config=am.PeakConfig(dist, prom), max_peaks_per_chunk=maxpk)
+    algo = am.CudaConvolve(snip, sr=sr, config=conf)
+    got = am.calc_chunks(sr, pcm, algo, True, conf, cap=1 << 18)
+    algo.close()
+    assert len(ref) > 0
+    _assert_peaks(got, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+
+
+def test_edge_cases(am, orc, native):
+    sr = 8000
+    snip = orc.synth_pcm16(7, 0, 4000)
+    conf = am.Config(chunk_size=5.0, peak_config=am.PeakConfig(2.0, 0.13))
+    algo = am.CudaConvolve(snip, sr=sr, config=conf)
+    assert am.calc_chunks(sr, np.zeros(0, np.int16), algo, True, conf) == []                 # empty stream
+    assert am.calc_chunks(sr, orc.synth_pcm16(8, 0, 3999), algo, True, conf) == []           # shorter than the snippet
+    assert am.calc_chunks(sr, np.zeros(100000, np.int16), algo, True, conf) == []            # silence: flat, no peaks
+    exact = snip.copy()                                                                      # stream == snippet: V = 1
+    assert am.calc_chunks(sr, exact, algo, True, conf) == []
+    assert algo.correlate_with_sample(np.zeros(10, np.float32), am.Mode.Valid).size == 0     # n < m
+    one = algo.correlate_with_sample(orc.pcm16_to_f32(snip), am.Mode.Valid, True)            # autocorrelation == 1
+    assert one.shape == (1,) and abs(one[0] - 1.0) < 1e-5
+    # capacity errors are loud
+    noisy = am.Config(chunk_size=5.0, peak_config=am.PeakConfig(0.0, 0.0), max_peaks_per_chunk=16)
+    with pytest.raises(native.NativeError) as e:
+        am.calc_chunks(sr, orc.synth_pcm16(9, 0, 80000), algo, True, noisy)
+    assert e.value.status == native.AM_ERR_CAPACITY
+    with pytest.raises(native.NativeError):
+        am.calc_chunks(sr, orc.synth_pcm16(9, 0, 80000), algo, True, am.Config(chunk_size=5.0, fft_log2=10))   # 2^10 < 2m
+    with pytest.raises(ValueError):
+        am.calc_chunks(sr + 1, orc.synth_pcm16(9, 0, 80000), algo, True, conf)               # SampleRateMismatch
+    algo.close()
+
+
+def test_stream_handle_is_shareable_between_threads(am, orc):
+    """calc_chunks calls correlate_with_sample concurrently on one shared &algo (audio_matcher.rs:114-122)."""
+    import threading
+    rng = np.random.default_rng(0)
+    s = rng.standard_normal(300).astype(np.float32)
+    ws = [rng.standard_normal(5000).astype(np.float32) for _ in range(8)]
+    algo = am.CudaConvolve(s, sr=1000)
+    out = [None] * 8
+
+    def work(i):
+        out[i] = algo.correlate_with_sample(ws[i], am.Mode.Valid, False)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(8):
+        assert _rel(out[i], orc.correlate(ws[i], s, orc.MODE_VALID, 0)) < 5e-6
+    algo.close()
+
+
+@pytest.fixture(scope="module")
+def full_size(am, orc, native):
+    """BASELINE.json configs[1]: one 10 s snippet vs a 24 h 48 kHz mono stream, generated on the device."""
+    import torch
+    sr, m, frames = 48000, 480000, 48000 * 86400
+    L = native.lib()
+    pcm = torch.empty(frames, dtype=torch.int16, device="cuda")
+    native.check(L.am_synth_pcm16_device(orc.SEED_STREAM, 0, frames, pcm.data_ptr(), None))
+    snip = orc.synth_pcm16(orc.SEED_SNIP, 0, m)
+    sd = torch.from_numpy(snip).cuda()
+    P, J, Cs = 600 * sr, 30 * sr, 60 * sr
+    planted = {}
+    k = 0
+    while k * P + m <= frames:
+        o = orc.plant_offset(k, P, J, Cs)
+        native.check(L.am_synth_plant_device(pcm.data_ptr(), frames, 1, sd.data_ptr(), m, o, k % 4, None))
+        planted[o] = k % 4
+        k += 1
+    torch.cuda.synchronize()
+    conf = am.Config(chunk_size=60.0, peak_config=am.PeakConfig(480.0, 0.13), fft_log2=22)
+    algo = am.CudaConvolve(snip, sr=sr, config=conf)
+    yield dict(sr=sr, m=m, frames=frames, pcm=pcm, snip=snip, planted=planted, conf=conf, algo=algo)
+    algo.close()
+
+
+def test_full_size_properties(am, orc, full_size):
+    fs = full_size
+    algo, conf, sr = fs["algo"], fs["conf"], fs["sr"]
+    whole = am.calc_chunks(sr, fs["pcm"], algo, True, conf)
+    starts = [p.position.start for p in whole]
+    assert len(starts) > 50 and starts == sorted(starts)
+    assert all(s in fs["planted"] for s in starts)                         # only planted offsets, exact sample positions
+    assert all(fs["planted"][s] <= 2 or p.prominence >= 0.13 for s, p in zip(starts, whole))
+    for p in whole:                                                        # score ~ gain of the planted copy
+        assert abs(p.height - 2.0 ** -fs["planted"][p.position.start]) < 0.02
+    # shard + merge == whole (the multi-GPU decomposition, chunk ranges with halo)
+    total = algo.num_chunks(fs["frames"])
+    parts = []
+    for r in range(3):
+        a, b = r * total // 3, (r + 1) * total // 3
+        parts += algo._calc(fs["pcm"], True, fs["frames"], 0, a, b - a, False, 1 << 16)
+    merged = am.merge_peaks(parts, sr, conf.peak_config.distance)
+    assert [p.position.start for p in merged] == starts                    # offsets exact; scores differ only by the
+    for a, b in zip(merged, whole):                                        # rounding of a different block tiling
+        assert abs(a.height - b.height) <= 1e-5 * abs(b.height) and abs(a.prominence - b.prominence) <= 1e-5 * abs(b.prominence)
+    # idempotence / determinism
+    again = am.calc_chunks(sr, fs["pcm"], algo, True, conf)
+    assert [(p.position.start, p.height) for p in again] == [(p.position.start, p.height) for p in whole]
+
+
+def test_full_size_chunks_vs_oracle(am, orc, full_size):
+    """Two logical chunks of the 24 h workload (block length 2^22, real data) against the oracle."""
+    fs = full_size
+    sr, m, Cs = fs["sr"], fs["m"], 60 * fs["sr"]
+    first, n = 9, 2                                                        # chunks 9-10 hold a planted copy (k = 1, 600 s)
+    lo, hi = first * Cs, (first + n) * Cs + m
+    host = fs["pcm"][lo:hi].cpu().numpy()
+    x, s = orc.pcm16_to_f32(host), orc.pcm16_to_f32(fs["snip"])
+    ref = orc.calc_chunks(x, s, sr, orc.make_config(60.0, m / sr, 480.0, 0.13), scale=True, precision=64, n_chunks=n,
+                          final_filter=False)
+    got = fs["algo"]._calc(fs["pcm"], True, fs["frames"], 0, first, n, False, 1 << 12)
+    assert len(ref) >= 1
+    assert sorted(p.position.start - lo for p in got) == sorted(p.start for p in ref)
+    gh = {p.position.start - lo: p for p in got}
+    for r in ref:
+        assert abs(gh[r.start].height - r.height) <= REL_TOL * abs(r.height)
+        assert abs(gh[r.start].prominence - r.prominence) <= REL_TOL * abs(r.prominence)
+
+
+def test_host_memory_path_equals_device_path(am, orc, full_size):
+    fs = full_size
+    import torch
+    frames = 48000 * 3600 * 2                                              # 2 h through the staged H2D path
+    host = torch.empty(frames, dtype=torch.int16, pin_memory=True)
+    host.copy_(fs["pcm"][:frames])
+    torch.cuda.synchronize()
+    a = am.calc_chunks(fs["sr"], host, fs["algo"], True, fs["conf"])
+    st = fs["algo"].stats()
+    b = am.calc_chunks(fs["sr"], fs["pcm"][:frames], fs["algo"], True, fs["conf"])
+    assert [(p.position.start, p.height, p.prominence) for p in a] == [(p.position.start, p.height, p.prominence) for p in b]
+    assert st["h2d_bytes"] >= frames * 2 and len(a) > 0
+
+
+def test_two_gpu_sharded_nccl(am):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(root, "bench.py"), "--gpus", "2", "--hours", "1", "--steps", "1", "--warmup", "1",
+           "--no-e2e"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and line["config"]["verified_offsets_are_planted"]

@@ -180,24 +180,31 @@ template <int MODE> am_status launch_small(am_matcher *h, int log2n, const amk::
     return fail(AM_ERR_UNSUPPORTED, "single-pass length 2^%d not built", log2n);
 }
 
-template <int L1, bool INV> am_status launch_col_t(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *A) {
-    typedef amk::ColCfg<L1> Cfg;
+template <int L1, int LT, bool INV> am_status launch_col_t(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *A) {
+    typedef amk::ColCfg<L1, LT> Cfg;
     int pairs = (g.nblocks + 1) / 2;
     dim3 grid((1u << l2) >> Cfg::LT, pairs);
     if (INV) {
-        TRY(set_smem(amk::k_col_inv<L1>, Cfg::SMEM));
-        LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
+        TRY(set_smem(amk::k_col_inv<L1, LT>, Cfg::SMEM));
+        LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
     } else {
-        TRY(set_smem(amk::k_col_fwd<L1>, Cfg::SMEM));
-        LAUNCH(h, AM_K_COL_FWD, amk::k_col_fwd<L1><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
+        TRY(set_smem(amk::k_col_fwd<L1, LT>, Cfg::SMEM));
+        LAUNCH(h, AM_K_COL_FWD, amk::k_col_fwd<L1, LT><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
     }
     return AM_OK;
 }
 template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::BlockGroup &g, int l2, float2 *A) {
+    static const int lt_env = [] { const char *v = getenv("AM_COL_LT"); return v && *v ? atoi(v) : 0; }();
     switch (l1) {
-#define C_(L) case L: return launch_col_t<L, INV>(h, g, l2, A);
-        C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11)
+#define C_(L) case L: return launch_col_t<L, amk::col_default_lt(L), INV>(h, g, l2, A);
+        C_(4) C_(5) C_(6) C_(7) C_(8) C_(11)
 #undef C_
+    case 9:                                   // tuning knob: tile of 8 or 16 columns
+        if (lt_env == 3) return launch_col_t<9, 3, INV>(h, g, l2, A);
+        return launch_col_t<9, 4, INV>(h, g, l2, A);
+    case 10:
+        if (lt_env == 4) return launch_col_t<10, 4, INV>(h, g, l2, A);
+        return launch_col_t<10, 3, INV>(h, g, l2, A);
     }
     return fail(AM_ERR_UNSUPPORTED, "column length 2^%d not built", l1);
 }
@@ -698,8 +705,11 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     TRY(h->d_tmin.reserve((size_t)(K * tiles_stride)));
     TRY(h->d_tmax.reserve((size_t)(K * tiles_stride)));
     const int pk_cap = h->cfg.max_peaks_per_chunk ? (int)h->cfg.max_peaks_per_chunk : 1024;
-    const size_t pk_smem = (size_t)pk_cap * (2 * sizeof(unsigned) + 4 * sizeof(float) + 1);
+    size_t pk_smem = (size_t)pk_cap * (2 * sizeof(unsigned) + 4 * sizeof(float) + 1);
     if (pk_smem > 200 * 1024) return fail(AM_ERR_INVALID, "max_peaks_per_chunk %d too large", pk_cap);
+    int sm_tiles = 0;                                        // tile summaries staged in shared memory when they fit
+    if (pk_smem + (size_t)tiles_stride * 8 <= 96 * 1024) sm_tiles = (int)tiles_stride;
+    pk_smem += (size_t)sm_tiles * 8;
     TRY(set_smem(amp::k_chunk_peaks, pk_smem));
     const size_t dev_cap = std::min<size_t>((size_t)num_chunks * (size_t)pk_cap, (size_t)1 << 22);
     TRY(h->d_peaks.reserve(dev_cap));
@@ -741,7 +751,7 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
         dim3 tgrid((unsigned)tiles_stride, (unsigned)(i1 - i0));
         LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p));
         LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<<<(unsigned)(i1 - i0), 256, pk_smem, h->stream>>>(
-                                        h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist, pk_cap, po));
+                                        h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist, pk_cap, sm_tiles, po));
     }
     unsigned long long cnt[2] = {0, 0};
     CU(cudaMemcpyAsync(cnt, h->d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));

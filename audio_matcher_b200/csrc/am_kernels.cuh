@@ -162,11 +162,13 @@ k_small(BlockGroup g, float2 *__restrict__ spec, const float2 *__restrict__ tw) 
 }
 
 // ---- four-step path ---------------------------------------------------------------
-template <int L1> struct ColCfg {
-    static constexpr int LT = (L1 >= 11) ? 3 : (L1 >= 7 ? 4 : 11 - L1);   // tile columns: N1*T >= 2048, <= 128 KB
+// default tile width (log2 columns): N1*T >= 2048 elements and <= 64 KB of exchange buffer
+constexpr int col_default_lt(int l1) { return l1 >= 10 ? 13 - l1 : (l1 >= 7 ? 4 : 11 - l1); }
+template <int L1, int LT_ = col_default_lt(L1)> struct ColCfg {
+    static constexpr int LT = LT_;
     static constexpr int T = 1 << LT;
     static constexpr int THREADS = ((1 << L1) * T) / EPT;
-    static constexpr int MINB = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : 1024 / THREADS);   // <= 64 registers
+    static constexpr int MINB = THREADS >= 1024 ? 1 : 1024 / THREADS;   // <= 64 registers
     static constexpr size_t SMEM = (size_t)RegFFT<L1, LT, false>::SMEM_ELEMS * sizeof(float2);
 };
 
@@ -207,10 +209,10 @@ __device__ __forceinline__ void load_tile_fast(float2 (&v)[EPT], const BlockGrou
 }
 
 // grid (N2 / T, pairs).  A[pair][k1][n2] = W_N^{n2 k1} * sum_{n1} z[n1 N2 + n2] W_N1^{n1 k1}
-template <int L1>
-__global__ void __launch_bounds__(ColCfg<L1>::THREADS, ColCfg<L1>::MINB)
+template <int L1, int LT>
+__global__ void __launch_bounds__(ColCfg<L1, LT>::THREADS, ColCfg<L1, LT>::MINB)
 k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__restrict__ tw) {
-    typedef ColCfg<L1> Cfg;
+    typedef ColCfg<L1, LT> Cfg;
     typedef RegFFT<L1, Cfg::LT, false> F;
     extern __shared__ float2 sm_all[];
     const int tid = threadIdx.x, pair = blockIdx.y;
@@ -247,10 +249,10 @@ k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__rest
 }
 
 // grid (N2 / T, pairs).  y[n1 N2 + n2] = sum_{k1} W_N1^{-n1 k1} W_N^{-n2 k1} B[k1][n2]
-template <int L1>
-__global__ void __launch_bounds__(ColCfg<L1>::THREADS, ColCfg<L1>::MINB)
+template <int L1, int LT>
+__global__ void __launch_bounds__(ColCfg<L1, LT>::THREADS, ColCfg<L1, LT>::MINB)
 k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *__restrict__ tw) {
-    typedef ColCfg<L1> Cfg;
+    typedef ColCfg<L1, LT> Cfg;
     typedef RegFFT<L1, Cfg::LT, true> I;
     extern __shared__ float2 sm_all[];
     const int tid = threadIdx.x, pair = blockIdx.y;

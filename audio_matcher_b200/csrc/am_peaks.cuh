@@ -53,22 +53,29 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// grid (tiles_stride, chunks in segment), 256 threads
+// grid (tiles_stride, chunks in segment), 256 threads: one 1024-sample tile per CTA, float4 loads
 __global__ void __launch_bounds__(256)
 k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin, float *__restrict__ tmax) {
     const long long chunk = g.first_chunk + blockIdx.y;
     const long long V = chunk_valid_len(g, chunk);
     const long long k0 = (long long)blockIdx.x << TP_LOG2;
     if (k0 >= V) return;
-    const float *y = c + (g.C * chunk - g.c_g0);
+    const float *y = c + (g.C * chunk - g.c_g0) + k0;
+    const long long left = V - k0;
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    if (left >= TP && (((size_t)y) & 15) == 0) {
+        float4 v = __ldg((const float4 *)y + threadIdx.x);
+        mn = fminf(fminf(v.x, v.y), fminf(v.z, v.w));
+        mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    } else {
 #pragma unroll
-    for (int i = 0; i < TP / 256; ++i) {
-        long long k = k0 + i * 256 + threadIdx.x;
-        if (k < V) {
-            float v = __ldg(y + k);
-            mn = fminf(mn, v);
-            mx = fmaxf(mx, v);
+        for (int i = 0; i < TP / 256; ++i) {
+            int k = i * 256 + threadIdx.x;
+            if (k < left) {
+                float v = __ldg(y + k);
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+            }
         }
     }
     mn = warp_min(mn);
@@ -77,6 +84,7 @@ k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin
     if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
     __syncthreads();
     if (threadIdx.x == 0) {
+#pragma unroll
         for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
         size_t o = (size_t)blockIdx.y * g.tiles_stride + blockIdx.x;
         tmin[o] = mn;
@@ -168,14 +176,15 @@ struct PeakOut {
     unsigned *flags;                // bit 0: per-chunk candidate list overflow
 };
 
-// dynamic shared memory: pk_cap * (2*u32 + 4*f32 + u8)
-// grid = chunks in segment, 256 threads
+// dynamic shared memory: [2 * sm_tiles floats: the chunk's tile summaries, when they fit] +
+// pk_cap * (2*u32 + 4*f32 + u8).   grid = chunks in segment, 256 threads
 __global__ void __launch_bounds__(256)
 k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict__ tmin_all,
               const float *__restrict__ tmax_all, float min_prom, unsigned long long min_dist, int pk_cap,
-              PeakOut out) {
+              int sm_tiles, PeakOut out) {
     extern __shared__ unsigned char smraw[];
-    unsigned *p_start = (unsigned *)smraw;
+    float *s_tmin = (float *)smraw, *s_tmax = s_tmin + sm_tiles;
+    unsigned *p_start = (unsigned *)(s_tmax + sm_tiles);
     unsigned *p_end = p_start + pk_cap;
     float *p_h = (float *)(p_end + pk_cap);
     float *p_prom = p_h + pk_cap;
@@ -195,6 +204,12 @@ k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict_
     const float *tmin = tmin_all + (size_t)blockIdx.x * g.tiles_stride;
     const float *tmax = tmax_all + (size_t)blockIdx.x * g.tiles_stride;
     const long long ntiles = (V + TP - 1) >> TP_LOG2;
+    if (ntiles <= sm_tiles) {                                       // stage the summaries: the walks re-read them
+        for (int t = tid; t < ntiles; t += 256) { s_tmin[t] = tmin[t]; s_tmax[t] = tmax[t]; }
+        __syncthreads();
+        tmin = s_tmin;
+        tmax = s_tmax;
+    }
 
     // (a) chunk minimum
     float mn = CUDART_INF_F;

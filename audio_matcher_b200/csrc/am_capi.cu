@@ -748,7 +748,7 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
         if (mem == AM_MEM_HOST) CU(cudaEventRecord(h->ev_done[seg_idx & 1], h->stream));
         amp::ChunkGeom cg;
         cg.C = C; cg.ov = ov; cg.m = m; cg.total = L; cg.first_chunk = i0; cg.c_g0 = g0; cg.tiles_stride = (int)tiles_stride;
-        dim3 tgrid((unsigned)tiles_stride, (unsigned)(i1 - i0));
+        dim3 tgrid((unsigned)((tiles_stride + 7) / 8), (unsigned)(i1 - i0));
         LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p));
         LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<<<(unsigned)(i1 - i0), 256, pk_smem, h->stream>>>(
                                         h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist, pk_cap, sm_tiles, po));

@@ -180,28 +180,50 @@ template <int LOG2N, int LOG2B, bool INV> struct RegFFT {
             dft<R, INV>(&v[l * R]);
         }
     }
-    // scatter stage ST's outputs into the exchange buffer (Stockham autosort index)
+    // scatter stage ST's outputs into the exchange buffer (Stockham autosort index).
+    // The padded slot of output s is slot(A) + a compile-time offset: A = j*Ns*R + k with k < Ns, so
+    // adding s*Ns never carries out of the low four bits that the padding term (i >> 4) drops.
     template <int ST> static AM_HD void xchg_write(const float2 (&v)[EPT], float2 *sm, int gtid) {
-        constexpr int RB = bits_at(ST), R = 1 << RB, NB = EPT / R, LOGNS = logns_at(ST);
+        constexpr int RB = bits_at(ST), R = 1 << RB, NB = EPT / R, LOGNS = logns_at(ST), NS = 1 << LOGNS;
 #pragma unroll
         for (int l = 0; l < NB; ++l) {
             int id = gtid + l * GT;
             int t = id & (B - 1), q = id >> LOG2B;
-            int k = q & ((1 << LOGNS) - 1);
+            int k = q & (NS - 1);
             int base = ((q - k) << RB) + k;
+            if constexpr (B == 1) {
+                const int sb = base + (base >> 4);
 #pragma unroll
-            for (int s = 0; s < R; ++s) sm[slot(((base + (s << LOGNS)) << LOG2B) + t)] = v[l * R + s];
+                for (int s = 0; s < R; ++s) sm[sb + s * NS + ((s * NS) >> 4)] = v[l * R + s];
+            } else if constexpr (B >= 16) {
+                const int sb = (base << LOG2B) + t;
+#pragma unroll
+                for (int s = 0; s < R; ++s) sm[sb + ((s * NS) << LOG2B)] = v[l * R + s];
+            } else {
+#pragma unroll
+                for (int s = 0; s < R; ++s) sm[slot(((base + (s << LOGNS)) << LOG2B) + t)] = v[l * R + s];
+            }
         }
     }
     // gather the inputs of stage ST (ST >= 1) from the exchange buffer
     template <int ST> static AM_HD void xchg_read(float2 (&v)[EPT], const float2 *sm, int gtid) {
-        constexpr int RB = bits_at(ST), R = 1 << RB, NB = EPT / R;
+        constexpr int RB = bits_at(ST), R = 1 << RB, NB = EPT / R, M = N >> RB;
 #pragma unroll
         for (int l = 0; l < NB; ++l) {
             int id = gtid + l * GT;
             int t = id & (B - 1), q = id >> LOG2B;
+            if constexpr (B == 1 && M >= 16) {
+                const int sb = q + (q >> 4);
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[l * R + r] = sm[slot(((q + r * (N >> RB)) << LOG2B) + t)];
+                for (int r = 0; r < R; ++r) v[l * R + r] = sm[sb + r * (M + M / 16)];
+            } else if constexpr (B >= 16) {
+                const int sb = (q << LOG2B) + t;
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[l * R + r] = sm[sb + ((r * M) << LOG2B)];
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[l * R + r] = sm[slot(((q + r * M) << LOG2B) + t)];
+            }
         }
     }
 

@@ -39,19 +39,16 @@ struct StreamView {
 };
 
 // exact int16 -> fp32 on the integer/FMA pipes (I2F.S16 runs on the slow conversion unit)
-__device__ __forceinline__ float s16_to_f32(int s) { return __int_as_float(0x4B400000 + s) - 12582912.0f; }
-// the reference's scale / downmix, mp3_reader.rs:12,35: (l + r) * 0.5 * (1/65535), mono: l = r
-__device__ __forceinline__ float pcm_scale(float l, float r) {
-    return __fmul_rn(__fmul_rn(__fadd_rn(l, r), 0.5f), 1.0f / 65535.0f);
-}
+__device__ __forceinline__ float s16_to_f32(int s) { return __int_as_float(0x4B400000 + s) - 12582912.0f; }   // |s| < 2^22
+// The reference's scale / downmix, mp3_reader.rs:12,35: fl(fl(fl(l + r) * 0.5) * (1/65535)), mono: l = r.
+// For 16-bit samples l + r and the halving are exact in fp32, so the value is the single rounding
+// fl((l + r) * (1/65535) / 2): one integer add, the exact int->float trick and one multiply.
+__device__ __forceinline__ float pcm_scale_sum(int l_plus_r) { return __fmul_rn(s16_to_f32(l_plus_r), 0.5f / 65535.0f); }
 template <int FMT> __device__ __forceinline__ float load_raw(const void *x, long long f) {
     if (FMT == FMT_F32_MONO) return __ldg((const float *)x + f);
-    if (FMT == FMT_I16_MONO) {
-        float a = s16_to_f32((int)__ldg((const short *)x + f));
-        return pcm_scale(a, a);
-    }
+    if (FMT == FMT_I16_MONO) return __fmul_rn(s16_to_f32((int)__ldg((const short *)x + f)), 1.0f / 65535.0f);
     short2 lr = __ldg((const short2 *)x + f);
-    return pcm_scale(s16_to_f32((int)lr.x), s16_to_f32((int)lr.y));
+    return pcm_scale_sum((int)lr.x + (int)lr.y);
 }
 
 __device__ __forceinline__ float load_frame(const StreamView &s, long long v) {
@@ -272,11 +269,28 @@ k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *
                        twiddle_big(n2 << (L1 - RB), two_over_n, true));
     }
     I::run(v, sm_all, tid, tw);
+    const long long o0 = g.g0 + (long long)(2 * pair) * g.VN;
+    if (2 * pair + 1 < g.nblocks && o0 + 2 * g.VN <= g.g_end) {
+        // both blocks entirely inside the requested output range (CTA-uniform): 32-bit crop test only
+        float *c0 = g.c + (o0 - g.c_g0);
+        const int vn = (int)g.VN;
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        int n1, t;
-        I::out_coord(tid, j, n1, t);
-        store_pair(g, pair, ((long long)n1 << log2n2) + n2_0 + t, v[j]);
+        for (int j = 0; j < EPT; ++j) {
+            int n1, t;
+            I::out_coord(tid, j, n1, t);
+            const int n = (n1 << log2n2) + n2_0 + t;
+            if (n < vn) {
+                c0[n] = v[j].x * g.scalar;
+                c0[n + vn] = v[j].y * g.scalar;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            int n1, t;
+            I::out_coord(tid, j, n1, t);
+            store_pair(g, pair, ((long long)n1 << log2n2) + n2_0 + t, v[j]);
+        }
     }
 }
 

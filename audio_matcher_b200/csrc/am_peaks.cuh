@@ -53,40 +53,39 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// grid (tiles_stride, chunks in segment), 256 threads: one 1024-sample tile per CTA, float4 loads
+// grid (ceil(tiles_stride / 8), chunks in segment), 256 threads: one 1024-sample tile per warp,
+// eight independent float4 loads in flight per lane
 __global__ void __launch_bounds__(256)
 k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin, float *__restrict__ tmax) {
     const long long chunk = g.first_chunk + blockIdx.y;
     const long long V = chunk_valid_len(g, chunk);
-    const long long k0 = (long long)blockIdx.x << TP_LOG2;
+    const int lane = threadIdx.x & 31;
+    const long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long k0 = tile << TP_LOG2;
     if (k0 >= V) return;
     const float *y = c + (g.C * chunk - g.c_g0) + k0;
     const long long left = V - k0;
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     if (left >= TP && (((size_t)y) & 15) == 0) {
-        float4 v = __ldg((const float4 *)y + threadIdx.x);
-        mn = fminf(fminf(v.x, v.y), fminf(v.z, v.w));
-        mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
-    } else {
+        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < TP / 256; ++i) {
-            int k = i * 256 + threadIdx.x;
-            if (k < left) {
-                float v = __ldg(y + k);
-                mn = fminf(mn, v);
-                mx = fmaxf(mx, v);
-            }
+        for (int i = 0; i < 8; ++i) v[i] = __ldg((const float4 *)y + i * 32 + lane);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            mn = fminf(mn, fminf(fminf(v[i].x, v[i].y), fminf(v[i].z, v[i].w)));
+            mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+        }
+    } else {
+        for (int k = lane; k < TP && k < left; k += 32) {
+            float v = __ldg(y + k);
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
         }
     }
     mn = warp_min(mn);
     mx = warp_max(mx);
-    __shared__ float smn[8], smx[8];
-    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
-        size_t o = (size_t)blockIdx.y * g.tiles_stride + blockIdx.x;
+    if (lane == 0) {
+        size_t o = (size_t)blockIdx.y * g.tiles_stride + tile;
         tmin[o] = mn;
         tmax[o] = mx;
     }

@@ -57,6 +57,9 @@ SYMBOLS = {
     "am_config_default": (None, [C.POINTER(AmConfig)]),
     "am_matcher_create": (C.c_int, [_VP, _SZ, C.c_uint32, C.POINTER(AmConfig), C.POINTER(_VP)]),
     "am_matcher_create_pcm16": (C.c_int, [_VP, _SZ, C.c_int, C.c_uint32, C.POINTER(AmConfig), C.POINTER(_VP)]),
+    "am_matcher_create_batch": (C.c_int, [_VP, _SZ, _SZ, C.c_uint32, C.POINTER(AmConfig), C.POINTER(_VP)]),
+    "am_matcher_snippet_count": (_SZ, [_VP]),
+    "am_matcher_select_snippet": (C.c_int, [_VP, _SZ]),
     "am_matcher_destroy": (None, [_VP]),
     "am_matcher_set_stream": (C.c_int, [_VP, _VP]),
     "am_matcher_set_config": (C.c_int, [_VP, C.POINTER(AmConfig)]),

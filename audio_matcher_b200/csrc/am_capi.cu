@@ -94,12 +94,14 @@ struct am_matcher {
     am_config cfg;
     uint32_t sr = 0;
     size_t m = 0;
-    DevBuf<float> d_snip;
-    double sumsq = 0.0;
-    float inv_ac = 0.f;
+    size_t S = 1;                            // snippets in the batch (all of m samples)
+    size_t active = 0;                       // snippet am_correlate / am_inverse_sample_auto_correlation use
+    DevBuf<float> d_snip;                    // [S][m]
+    std::vector<double> sumsq;
+    std::vector<float> inv_ac;
     DevBuf<float2> d_tw;
-    std::map<int, float2 *> spectra;
-    DevBuf<float2> d_A;
+    std::map<int, float2 *> spectra;         // log2n -> [S][N] conjugate spectra
+    DevBuf<float2> d_A, d_B;
     DevBuf<float> d_c, d_tmin, d_tmax;
     DevBuf<amp::DevPeak> d_peaks;
     DevBuf<unsigned long long> d_count;   // [0] = count, [1] low 32 bits = flags
@@ -163,17 +165,17 @@ void prof_collect(am_matcher *h) {
     } while (0)
 
 // ---- kernel dispatch ----------------------------------------------------------------
-template <int LOG2N, int MODE> am_status launch_small_t(am_matcher *h, const amk::BlockGroup &g, float2 *spec) {
+template <int LOG2N> am_status launch_small_t(am_matcher *h, const amk::BlockGroup &g, const float2 *spec) {
     typedef amk::SmallCfg<LOG2N> Cfg;
-    TRY(set_smem(amk::k_small<LOG2N, MODE>, Cfg::SMEM));
+    TRY(set_smem(amk::k_small<LOG2N>, Cfg::SMEM));
     int pairs = (g.nblocks + 1) / 2;
     int grid = (pairs + Cfg::G - 1) / Cfg::G;
-    LAUNCH(h, AM_K_SMALL, amk::k_small<LOG2N, MODE><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, spec, h->d_tw.p));
+    LAUNCH(h, AM_K_SMALL, amk::k_small<LOG2N><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, spec, h->d_tw.p));
     return AM_OK;
 }
-template <int MODE> am_status launch_small(am_matcher *h, int log2n, const amk::BlockGroup &g, float2 *spec) {
+am_status launch_small(am_matcher *h, int log2n, const amk::BlockGroup &g, const float2 *spec) {
     switch (log2n) {
-#define C_(L) case L: return launch_small_t<L, MODE>(h, g, spec);
+#define C_(L) case L: return launch_small_t<L>(h, g, spec);
         C_(4) C_(5) C_(6) C_(7) C_(8) C_(9) C_(10) C_(11) C_(12) C_(13)
 #undef C_
     }
@@ -209,16 +211,17 @@ template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::Block
     return fail(AM_ERR_UNSUPPORTED, "column length 2^%d not built", l1);
 }
 
-template <int L2, int MODE> am_status launch_row_t(am_matcher *h, float2 *A, float2 *spec, int l1, int rows) {
+template <int L2, int MODE>
+am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, int l1, int rows) {
     typedef amk::RowCfg<L2> Cfg;
     TRY(set_smem(amk::k_row<L2, MODE>, Cfg::SMEM));
     int grid = (rows + Cfg::G - 1) / Cfg::G;
-    LAUNCH(h, AM_K_ROW, amk::k_row<L2, MODE><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(A, spec, l1, rows, h->d_tw.p));
+    LAUNCH(h, AM_K_ROW, amk::k_row<L2, MODE><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(A, spec, B, l1, rows, h->d_tw.p));
     return AM_OK;
 }
-template <int MODE> am_status launch_row(am_matcher *h, int l2, float2 *A, float2 *spec, int l1, int rows) {
+template <int MODE> am_status launch_row(am_matcher *h, int l2, float2 *A, const float2 *spec, float2 *B, int l1, int rows) {
     switch (l2) {
-#define C_(L) case L: return launch_row_t<L, MODE>(h, A, spec, l1, rows);
+#define C_(L) case L: return launch_row_t<L, MODE>(h, A, spec, B, l1, rows);
         C_(10) C_(11) C_(12) C_(13)
 #undef C_
     }
@@ -257,9 +260,9 @@ am_status choose_log2n(const am_matcher *h, unsigned long long outputs, int &log
     return AM_OK;
 }
 
-amk::StreamView snippet_view(const am_matcher *h) {
+amk::StreamView snippet_view(const am_matcher *h, size_t snippet = 0) {
     amk::StreamView sv;
-    sv.x = h->d_snip.p;
+    sv.x = h->d_snip.p + snippet * h->m;
     sv.fmt = amk::FMT_F32_MONO;
     sv.buf_first = 0;
     sv.buf_frames = (long long)h->m;
@@ -275,6 +278,7 @@ am_status ensure_workspace(am_matcher *h, int log2n, unsigned long long pairs_to
     g = std::min<unsigned long long>(g, pairs_total);
     g = std::min<unsigned long long>(g, 32768);
     TRY(h->d_A.reserve((size_t)g << log2n));
+    if (h->S > 1) TRY(h->d_B.reserve((size_t)g << log2n));
     pairs_per_group = g;
     return AM_OK;
 }
@@ -290,22 +294,24 @@ am_status get_spectrum(am_matcher *h, int log2n, float2 **out) {
     split(log2n, l1, l2);
     float2 *spec = nullptr;
     double2 *buf = nullptr;
-    CU(cudaMalloc((void **)&spec, sizeof(float2) << log2n));
+    CU(cudaMalloc((void **)&spec, h->S * (sizeof(float2) << log2n)));
     cudaError_t e = cudaMalloc((void **)&buf, 2 * (sizeof(double2) << log2n));
     if (e != cudaSuccess) { cudaFree(spec); return fail(AM_ERR_NOMEM, "spectrum scratch: %s", cudaGetErrorString(e)); }
-    double2 *a = buf, *b = buf + n;
     const unsigned grid_n = (unsigned)((n + 255) / 256), grid_h = (unsigned)((n / 2 + 255) / 256);
-    prof_begin(h, AM_K_SPECTRUM);
-    amk::k_spec64_load<<<grid_n, 256, 0, h->stream>>>(snippet_view(h), n, a);
-    h->stats.kernel_launches++;
-    for (long long ns = 1; ns < n; ns <<= 1) {
-        amk::k_spec64_pass<<<grid_h, 256, 0, h->stream>>>(a, b, n / 2, ns);
+    for (size_t sn = 0; sn < h->S; ++sn) {
+        double2 *a = buf, *b = buf + n;
+        prof_begin(h, AM_K_SPECTRUM);
+        amk::k_spec64_load<<<grid_n, 256, 0, h->stream>>>(snippet_view(h, sn), n, a);
         h->stats.kernel_launches++;
-        std::swap(a, b);
+        for (long long ns = 1; ns < n; ns <<= 1) {
+            amk::k_spec64_pass<<<grid_h, 256, 0, h->stream>>>(a, b, n / 2, ns);
+            h->stats.kernel_launches++;
+            std::swap(a, b);
+        }
+        amk::k_spec64_store<<<grid_n, 256, 0, h->stream>>>(a, n, l1, l1 ? l2 : 0, spec + sn * (size_t)n);
+        h->stats.kernel_launches++;
+        prof_end(h);
     }
-    amk::k_spec64_store<<<grid_n, 256, 0, h->stream>>>(a, n, l1, l1 ? l2 : 0, spec);
-    h->stats.kernel_launches++;
-    prof_end(h);
     e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaGetLastError();
     cudaFree(buf);
@@ -315,21 +321,27 @@ am_status get_spectrum(am_matcher *h, int log2n, float2 **out) {
     return AM_OK;
 }
 
-// correlation outputs [g0, g1) (virtual offsets) -> c[g - c_g0]
-am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0, long long g1, int log2n,
-                          float scalar, float *c, long long c_g0) {
-    if (g1 <= g0) return AM_OK;
+// correlation outputs [g0, g1) (virtual offsets) of snippets [s0, s0 + ns) -> c[j * c_stride + g - c_g0].
+// With several snippets the stream-side work (column pass + forward row pass) is done once per block
+// group and only the multiply + inverse passes run per snippet.
+am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0, long long g1, int log2n, int scale,
+                          float *c, size_t c_stride, long long c_g0, size_t s0, size_t ns) {
+    if (g1 <= g0 || ns == 0) return AM_OK;
+    const float inv_n = (float)(1.0 / (double)(1ull << log2n));
+    auto scalar_of = [&](size_t sn) { return inv_n * (scale ? h->inv_ac[sn] : 1.0f); };
     if (h->m <= (size_t)amk::DIRECT_MAX_M && !getenv("AM_NO_DIRECT")) {
-        // very short snippet: direct sums; `scalar` carries 1/N for the transform paths
-        const float sc = scalar * (float)(1ull << log2n);
+        // very short snippet: direct sums
         const unsigned long long nb = (unsigned long long)(g1 - g0 + 255) / 256;
         if (nb > 0x7fffffffull) return fail(AM_ERR_UNSUPPORTED, "direct path: too many outputs");
-        LAUNCH(h, AM_K_DIRECT, amk::k_direct<<<(unsigned)nb, 256, 0, h->stream>>>(sv, h->d_snip.p, (int)h->m, g0, g1, c, c_g0, sc));
+        for (size_t j = 0; j < ns; ++j)
+            LAUNCH(h, AM_K_DIRECT, amk::k_direct<<<(unsigned)nb, 256, 0, h->stream>>>(
+                                       sv, h->d_snip.p + (s0 + j) * h->m, (int)h->m, g0, g1, c + j * c_stride, c_g0,
+                                       scale ? h->inv_ac[s0 + j] : 1.0f));
         h->stats.fft_log2 = 0; h->stats.log2_n1 = 0; h->stats.log2_n2 = 0;
         return AM_OK;
     }
-    float2 *spec;
-    TRY(get_spectrum(h, log2n, &spec));
+    float2 *spec_all;
+    TRY(get_spectrum(h, log2n, &spec_all));
     const long long N = 1ll << log2n, VN = N - (long long)h->m + 1;
     const unsigned long long nblocks = (unsigned long long)((g1 - g0 + VN - 1) / VN);
     const unsigned long long pairs_total = (nblocks + 1) / 2;
@@ -338,19 +350,32 @@ am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0
     h->stats.fft_log2 = log2n; h->stats.log2_n1 = l1; h->stats.log2_n2 = l2;
     h->stats.fft_blocks += nblocks;
     amk::BlockGroup g;
-    g.sv = sv; g.g_end = g1; g.VN = VN; g.c = c; g.c_g0 = c_g0; g.scalar = scalar;
+    g.sv = sv; g.g_end = g1; g.VN = VN; g.c = c; g.c_g0 = c_g0; g.scalar = 0.f;
     unsigned long long ppg = 1u << 20;     // pairs per launch
     if (l1 != 0) TRY(ensure_workspace(h, log2n, pairs_total, ppg));
     for (unsigned long long p0 = 0; p0 < pairs_total; p0 += ppg) {
         unsigned long long np = std::min(ppg, pairs_total - p0);
         g.g0 = g0 + (long long)(2 * p0) * VN;
         g.nblocks = (int)std::min<unsigned long long>(2 * np, nblocks - 2 * p0);
+        const int rows = (int)(np << l1);
         if (l1 == 0) {
-            TRY(launch_small<0>(h, log2n, g, spec));
+            for (size_t j = 0; j < ns; ++j) {
+                g.c = c + j * c_stride; g.scalar = scalar_of(s0 + j);
+                TRY(launch_small(h, log2n, g, spec_all + (s0 + j) * (size_t)N));
+            }
+        } else if (ns == 1) {
+            g.c = c; g.scalar = scalar_of(s0);
+            TRY(launch_col<false>(h, l1, g, l2, h->d_A.p));
+            TRY(launch_row<amk::ROW_FUSED>(h, l2, h->d_A.p, spec_all + s0 * (size_t)N, nullptr, l1, rows));
+            TRY(launch_col<true>(h, l1, g, l2, h->d_A.p));
         } else {
             TRY(launch_col<false>(h, l1, g, l2, h->d_A.p));
-            TRY(launch_row<0>(h, l2, h->d_A.p, spec, l1, (int)(np << l1)));
-            TRY(launch_col<true>(h, l1, g, l2, h->d_A.p));
+            TRY(launch_row<amk::ROW_FORWARD>(h, l2, h->d_A.p, nullptr, nullptr, l1, rows));
+            for (size_t j = 0; j < ns; ++j) {
+                g.c = c + j * c_stride; g.scalar = scalar_of(s0 + j);
+                TRY(launch_row<amk::ROW_INVERSE>(h, l2, h->d_A.p, spec_all + (s0 + j) * (size_t)N, h->d_B.p, l1, rows));
+                TRY(launch_col<true>(h, l1, g, l2, h->d_B.p));
+            }
         }
     }
     return AM_OK;
@@ -377,13 +402,18 @@ am_status init_common(am_matcher *h, uint32_t sr, const am_config *cfg) {
     TRY(h->d_tw.reserve(amfft::TW_N));
     CU(cudaMemcpy(h->d_tw.p, tw.data(), sizeof(float2) * amfft::TW_N, cudaMemcpyHostToDevice));
     TRY(h->d_count.reserve(2));
-    // sum s^2 on the device (double accumulation)
+    // sum s^2 per snippet on the device (double accumulation)
+    h->sumsq.assign(h->S, 0.0);
+    h->inv_ac.assign(h->S, 0.f);
     double *d_acc = (double *)h->d_count.p;
-    CU(cudaMemsetAsync(d_acc, 0, sizeof(double), h->stream));
-    LAUNCH(h, AM_K_SPECTRUM, amk::k_sumsq<<<(unsigned)std::min<size_t>(1024, (h->m + 255) / 256), 256, 0, h->stream>>>(snippet_view(h), (long long)h->m, d_acc));
-    CU(cudaMemcpyAsync(&h->sumsq, d_acc, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    h->inv_ac = (float)(1.0 / h->sumsq);
+    for (size_t sn = 0; sn < h->S; ++sn) {
+        CU(cudaMemsetAsync(d_acc, 0, sizeof(double), h->stream));
+        LAUNCH(h, AM_K_SPECTRUM, amk::k_sumsq<<<(unsigned)std::min<size_t>(1024, (h->m + 255) / 256), 256, 0, h->stream>>>(
+                                     snippet_view(h, sn), (long long)h->m, d_acc));
+        CU(cudaMemcpyAsync(&h->sumsq[sn], d_acc, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->inv_ac[sn] = (float)(1.0 / h->sumsq[sn]);
+    }
     return AM_OK;
 }
 
@@ -458,20 +488,23 @@ size_t am_out_len(size_t n, size_t m, am_mode mode) {
     }
 }
 
-static am_status create_impl(const void *data, size_t m, int fmt, uint32_t sr, const am_config *cfg, am_matcher **out) {
+static am_status create_impl(const void *data, size_t m, size_t S, int fmt, uint32_t sr, const am_config *cfg,
+                             am_matcher **out) {
     if (!out) return fail(AM_ERR_INVALID, "out is NULL");
     *out = nullptr;
-    if (!data || m == 0) return fail(AM_ERR_INVALID, "empty snippet");
+    if (!data || m == 0 || S == 0) return fail(AM_ERR_INVALID, "empty snippet");
+    if (S > 4096) return fail(AM_ERR_INVALID, "too many snippets in one batch (%zu)", S);
     if (sr == 0) return fail(AM_ERR_INVALID, "sample rate 0");
     if (m > (1ull << (MAX_LOG2 - 1))) return fail(AM_ERR_UNSUPPORTED, "snippet of %zu samples exceeds 2^%d", m, MAX_LOG2 - 1);
     if (am_device_count() == 0) return fail(AM_ERR_CUDA, "no CUDA device visible (this library has no CPU fallback)");
     am_matcher *h = new (std::nothrow) am_matcher();
     if (!h) return fail(AM_ERR_NOMEM, "out of host memory");
     h->m = m;
-    am_status st = h->d_snip.reserve(m);
+    h->S = S;
+    am_status st = h->d_snip.reserve(m * S);
     if (st == AM_OK) {
         if (fmt == AM_FMT_F32_MONO) {
-            cudaError_t e = cudaMemcpy(h->d_snip.p, data, m * sizeof(float), cudaMemcpyHostToDevice);
+            cudaError_t e = cudaMemcpy(h->d_snip.p, data, m * S * sizeof(float), cudaMemcpyHostToDevice);
             if (e != cudaSuccess) st = fail(AM_ERR_CUDA, "snippet upload: %s", cudaGetErrorString(e));
         } else {
             // scale / downmix on the device with the same load path the stream uses
@@ -495,12 +528,24 @@ static am_status create_impl(const void *data, size_t m, int fmt, uint32_t sr, c
 }
 
 am_status am_matcher_create(const float *snippet, size_t m, uint32_t sr, const am_config *cfg, am_matcher **out) {
-    return create_impl(snippet, m, AM_FMT_F32_MONO, sr, cfg, out);
+    return create_impl(snippet, m, 1, AM_FMT_F32_MONO, sr, cfg, out);
+}
+am_status am_matcher_create_batch(const float *snippets, size_t m, size_t n_snippets, uint32_t sr, const am_config *cfg,
+                                  am_matcher **out) {
+    return create_impl(snippets, m, n_snippets, AM_FMT_F32_MONO, sr, cfg, out);
+}
+size_t am_matcher_snippet_count(const am_matcher *h) { return h ? h->S : 0; }
+am_status am_matcher_select_snippet(am_matcher *h, size_t snippet_id) {
+    if (!h) return fail(AM_ERR_INVALID, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (snippet_id >= h->S) return fail(AM_ERR_INVALID, "snippet %zu of %zu", snippet_id, h->S);
+    h->active = snippet_id;
+    return AM_OK;
 }
 am_status am_matcher_create_pcm16(const int16_t *pcm, size_t frames, int channels, uint32_t sr, const am_config *cfg,
                                   am_matcher **out) {
     if (channels != 1 && channels != 2) return fail(AM_ERR_INVALID, "channels must be 1 or 2");
-    return create_impl(pcm, frames, channels == 2 ? AM_FMT_I16_STEREO : AM_FMT_I16_MONO, sr, cfg, out);
+    return create_impl(pcm, frames, 1, channels == 2 ? AM_FMT_I16_STEREO : AM_FMT_I16_MONO, sr, cfg, out);
 }
 
 void am_matcher_destroy(am_matcher *h) {
@@ -508,7 +553,7 @@ void am_matcher_destroy(am_matcher *h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (auto &kv : h->spectra) cudaFree(kv.second);
-    h->d_snip.release(); h->d_tw.release(); h->d_A.release(); h->d_c.release(); h->d_tmin.release();
+    h->d_snip.release(); h->d_tw.release(); h->d_A.release(); h->d_B.release(); h->d_c.release(); h->d_tmin.release();
     h->d_tmax.release(); h->d_peaks.release(); h->d_count.release();
     h->d_stage[0].release(); h->d_stage[1].release();
     for (int i = 0; i < 2; ++i) {
@@ -569,7 +614,7 @@ am_status am_matcher_get_kernel_times(const am_matcher *h, am_kernel_time *out, 
 
 am_status am_inverse_sample_auto_correlation(am_matcher *h, float *out) {
     if (!h || !out) return fail(AM_ERR_INVALID, "NULL argument");
-    *out = h->inv_ac;
+    *out = h->inv_ac[h->active];
     return AM_OK;
 }
 
@@ -603,8 +648,7 @@ am_status am_correlate(am_matcher *h, const void *within, size_t n, am_sample_fm
     }
     int log2n;
     TRY(choose_log2n(h, olen, log2n));
-    const float scalar = (float)(1.0 / (double)(1ull << log2n)) * (scale ? h->inv_ac : 1.0f);
-    TRY(run_correlation(h, sv, 0, (long long)olen, log2n, scalar, d_out, 0));
+    TRY(run_correlation(h, sv, 0, (long long)olen, log2n, scale, d_out, 0, 0, h->active, 1));
     if (out_mem == AM_MEM_HOST) {
         CU(cudaMemcpyAsync(out, d_out, olen * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         h->stats.d2h_bytes += olen * sizeof(float);
@@ -640,9 +684,10 @@ am_status am_merge_peaks(am_peak *peaks, size_t n, uint32_t sr, double distance_
     if (!n_out || (n && (!peaks || !out))) return fail(AM_ERR_INVALID, "NULL argument");
     if (sr == 0) return fail(AM_ERR_INVALID, "sample rate 0");
     // sorted_by position.start (stable, audio_matcher.rs:135); equal starts keep chunk order
+    // (a batch is handled as independent runs: snippet-major, neighbours only within a snippet)
     std::stable_sort(peaks, peaks + n, [](const am_peak &a, const am_peak &b) {
-        if (a.start != b.start) return a.start < b.start;
         if (a.snippet_id != b.snippet_id) return a.snippet_id < b.snippet_id;
+        if (a.start != b.start) return a.start < b.start;
         return a.chunk < b.chunk;
     });
     size_t k = 0;
@@ -693,14 +738,16 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     if (outputs == 0) return AM_OK;                          // every window shorter than the snippet
     int log2n;
     TRY(choose_log2n(h, outputs, log2n));
-    const float scalar = (float)(1.0 / (double)(1ull << log2n)) * (scale ? h->inv_ac : 1.0f);
 
-    // segments of K logical chunks share one dense correlation buffer
-    const size_t seg_floats = (env_mb("AM_SEGMENT_MB", 1024) << 20) / sizeof(float);
+    // segments of K logical chunks share one dense correlation buffer per snippet; a batch keeps at
+    // least ~48 M outputs per snippet per segment so that a segment still spans several block pairs
+    const size_t S = h->S;
+    size_t seg_floats = (env_mb("AM_SEGMENT_MB", 1024) << 20) / sizeof(float) / S;
+    if (S > 1) seg_floats = std::max<size_t>(seg_floats, (size_t)48 << 20);
     long long K = std::max<long long>(1, (long long)(seg_floats / (size_t)C));
     K = std::min<long long>(K, (long long)num_chunks);
-    const long long seg_c_len = K * C + std::max<long long>(ov - m + 1, 0) + 1;
-    TRY(h->d_c.reserve((size_t)seg_c_len));
+    const long long seg_c_len = ((K * C + std::max<long long>(ov - m + 1, 0) + 1 + 3) / 4) * 4;   // keeps float4 alignment per snippet
+    TRY(h->d_c.reserve((size_t)seg_c_len * S));
     const long long tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
     TRY(h->d_tmin.reserve((size_t)(K * tiles_stride)));
     TRY(h->d_tmax.reserve((size_t)(K * tiles_stride)));
@@ -711,7 +758,7 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     if (pk_smem + (size_t)tiles_stride * 8 <= 96 * 1024) sm_tiles = (int)tiles_stride;
     pk_smem += (size_t)sm_tiles * 8;
     TRY(set_smem(amp::k_chunk_peaks, pk_smem));
-    const size_t dev_cap = std::min<size_t>((size_t)num_chunks * (size_t)pk_cap, (size_t)1 << 22);
+    const size_t dev_cap = std::min<size_t>((size_t)num_chunks * (size_t)pk_cap * S, (size_t)1 << 22);
     TRY(h->d_peaks.reserve(dev_cap));
     CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
     amp::PeakOut po;
@@ -744,14 +791,18 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
         } else {
             sv.x = stream; sv.buf_first = (long long)buf_first_frame; sv.buf_frames = (long long)buf_frames;
         }
-        TRY(run_correlation(h, sv, g0, g1, log2n, scalar, h->d_c.p, g0));
+        TRY(run_correlation(h, sv, g0, g1, log2n, scale, h->d_c.p, (size_t)seg_c_len, g0, 0, S));
         if (mem == AM_MEM_HOST) CU(cudaEventRecord(h->ev_done[seg_idx & 1], h->stream));
         amp::ChunkGeom cg;
         cg.C = C; cg.ov = ov; cg.m = m; cg.total = L; cg.first_chunk = i0; cg.c_g0 = g0; cg.tiles_stride = (int)tiles_stride;
         dim3 tgrid((unsigned)((tiles_stride + 7) / 8), (unsigned)(i1 - i0));
-        LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p));
-        LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<<<(unsigned)(i1 - i0), 256, pk_smem, h->stream>>>(
-                                        h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist, pk_cap, sm_tiles, po));
+        for (size_t sn = 0; sn < S; ++sn) {
+            const float *cs = h->d_c.p + sn * (size_t)seg_c_len;
+            LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid, 256, 0, h->stream>>>(cs, cg, h->d_tmin.p, h->d_tmax.p));
+            LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<<<(unsigned)(i1 - i0), 256, pk_smem, h->stream>>>(
+                                            cs, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist, pk_cap, sm_tiles,
+                                            (unsigned)sn, po));
+        }
     }
     unsigned long long cnt[2] = {0, 0};
     CU(cudaMemcpyAsync(cnt, h->d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
@@ -770,6 +821,7 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     }
     if (!final_filter) {
         std::stable_sort(all.begin(), all.end(), [](const am_peak &a, const am_peak &b) {
+            if (a.snippet_id != b.snippet_id) return a.snippet_id < b.snippet_id;
             if (a.chunk != b.chunk) return a.chunk < b.chunk;
             return a.height > b.height || (a.height == b.height && a.start < b.start);
         });

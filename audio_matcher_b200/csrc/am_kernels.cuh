@@ -10,7 +10,8 @@
 //       k_col_fwd  PCM -> f32 (scale/downmix fused into the load, mp3_reader.rs:12,35),
 //                  length-N1 column transforms over a tile of T columns, twiddle, store A[k1][n2]
 //       k_row      per row k1: length-N2 transform, multiply by the conjugate snippet
-//                  spectrum, inverse transform, all in registers; in-place on A
+//                  spectrum, inverse transform, all in registers; in-place on A (for a batch of
+//                  snippets the forward transform runs once and the multiply+inverse per snippet)
 //       k_col_inv  conjugate twiddle, inverse column transforms, crop to the valid
 //                  outputs, scale by 1/(N sum s^2), store the correlation
 //
@@ -98,7 +99,6 @@ __device__ __forceinline__ float2 load_pair(const BlockGroup &g, int pair, long 
 }
 
 // ---- single-pass path -------------------------------------------------------------
-// MODE 0: correlate a block pair.  MODE 1: spectrum of the zero-padded snippet -> conj -> spec.
 template <int LOG2N> struct SmallCfg {
     static constexpr int N = 1 << LOG2N;
     static constexpr int GT = N / EPT;                       // threads per transform
@@ -107,9 +107,10 @@ template <int LOG2N> struct SmallCfg {
     static constexpr size_t SMEM = (size_t)G * RegFFT<LOG2N, 0, false>::SMEM_ELEMS * sizeof(float2);
 };
 
-template <int LOG2N, int MODE>
+// one thread group per block pair: load, transform, multiply by the snippet spectrum, inverse, crop
+template <int LOG2N>
 __global__ void __launch_bounds__(SmallCfg<LOG2N>::THREADS)
-k_small(BlockGroup g, float2 *__restrict__ spec, const float2 *__restrict__ tw) {
+k_small(BlockGroup g, const float2 *__restrict__ spec, const float2 *__restrict__ tw) {
     typedef RegFFT<LOG2N, 0, false> F;
     typedef RegFFT<LOG2N, 0, true> I;
     typedef SmallCfg<LOG2N> Cfg;
@@ -129,17 +130,6 @@ k_small(BlockGroup g, float2 *__restrict__ spec, const float2 *__restrict__ tw) 
         v[j] = load_pair(g, pair, idx);
     }
     F::run(v, sm, gtid, tw);
-    if constexpr (MODE == 1) {
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                int idx, t;
-                F::out_coord(gtid, j, idx, t);
-                spec[idx] = make_float2(v[j].x, -v[j].y);
-            }
-        }
-        return;
-    }
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
         int idx, t;
@@ -303,11 +293,15 @@ template <int L2> struct RowCfg {
     static constexpr size_t SMEM = (size_t)G * RegFFT<L2, 0, false>::SMEM_ELEMS * sizeof(float2);
 };
 
-// rows = pairs * N1.  MODE 0: A[row] <- IFFT(FFT(A[row]) * spec[k1]) in place.
-// MODE 1: spec[row] <- conj(FFT(A[row]))  (snippet spectrum, one "pair").
+// rows = pairs * N1, row r of A holds A[pair][k1][0..N2).
+//   ROW_FUSED    A[row] <- IFFT(FFT(A[row]) * spec[k1])            one snippet, in place
+//   ROW_FORWARD  A[row] <- FFT(A[row])                             many snippets: shared stream spectrum
+//   ROW_INVERSE  Bout[row] <- IFFT(A[row] * spec[k1])              ... then once per snippet
+enum { ROW_FUSED = 0, ROW_FORWARD = 2, ROW_INVERSE = 3 };
 template <int L2, int MODE>
 __global__ void __launch_bounds__(RowCfg<L2>::THREADS, RowCfg<L2>::MINB)
-k_row(float2 *__restrict__ A, float2 *__restrict__ spec, int log2n1, int rows, const float2 *__restrict__ tw) {
+k_row(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restrict__ Bout, int log2n1, int rows,
+      const float2 *__restrict__ tw) {
     typedef RegFFT<L2, 0, false> F;
     typedef RegFFT<L2, 0, true> I;
     typedef RowCfg<L2> Cfg;
@@ -319,40 +313,44 @@ k_row(float2 *__restrict__ A, float2 *__restrict__ spec, int log2n1, int rows, c
     if (!active) row = rows - 1;
     float2 *Ar = A + ((size_t)row << L2);
     float2 v[EPT];
+    if constexpr (MODE != ROW_INVERSE) {
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        int idx, t;
-        F::template in_coord<0>(gtid, j, idx, t);
-        v[j] = Ar[idx];
-    }
-    F::run(v, sm, gtid, tw);
-    const int k1 = row & ((1 << log2n1) - 1);
-    float2 *Sr = spec + ((size_t)k1 << L2);
-    if constexpr (MODE == 1) {
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                int idx, t;
-                F::out_coord(gtid, j, idx, t);
-                Sr[idx] = make_float2(v[j].x, -v[j].y);
-            }
+        for (int j = 0; j < EPT; ++j) {
+            int idx, t;
+            F::template in_coord<0>(gtid, j, idx, t);
+            v[j] = Ar[idx];
         }
-        return;
+        F::run(v, sm, gtid, tw);
+        if constexpr (MODE == ROW_FORWARD) {
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) {
+                    int idx, t;
+                    F::out_coord(gtid, j, idx, t);
+                    Ar[idx] = v[j];
+                }
+            }
+            return;
+        }
     }
+    const int k1 = row & ((1 << log2n1) - 1);
+    const float2 *Sr = spec + ((size_t)k1 << L2);
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {
         int idx, t;
-        F::out_coord(gtid, j, idx, t);
+        I::template in_coord<0>(gtid, j, idx, t);            // == F::out_coord: no exchange across the multiply
+        if constexpr (MODE == ROW_INVERSE) v[j] = Ar[idx];
         v[j] = amfft::cmul(v[j], __ldg(&Sr[idx]));
     }
-    __syncthreads();
+    if constexpr (MODE == ROW_FUSED) __syncthreads();        // exchange buffer is reused by the inverse
     I::run(v, sm, gtid, tw);
+    float2 *Or = (MODE == ROW_INVERSE) ? Bout + ((size_t)row << L2) : Ar;
     if (active) {
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             int idx, t;
             I::out_coord(gtid, j, idx, t);
-            Ar[idx] = v[j];
+            Or[idx] = v[j];
         }
     }
 }

@@ -180,7 +180,7 @@ struct PeakOut {
 __global__ void __launch_bounds__(256)
 k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict__ tmin_all,
               const float *__restrict__ tmax_all, float min_prom, unsigned long long min_dist, int pk_cap,
-              int sm_tiles, PeakOut out) {
+              int sm_tiles, unsigned snippet_id, PeakOut out) {
     extern __shared__ unsigned char smraw[];
     float *s_tmin = (float *)smraw, *s_tmax = s_tmin + sm_tiles;
     unsigned *p_start = (unsigned *)(s_tmax + sm_tiles);
@@ -283,7 +283,7 @@ k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict_
             p.prominence = p_prom[i];
             p.left_diff = p_ld[i];
             p.right_diff = p_rd[i];
-            p.snippet_id = 0;
+            p.snippet_id = snippet_id;
             p.chunk = (unsigned)chunk;
             out.peaks[slot] = p;
         }

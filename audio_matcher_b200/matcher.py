@@ -119,7 +119,24 @@ class CudaConvolve:
     """CorrelateAlgo<f32> (audio_matcher.rs:65-76) backed by the CUDA library: the drop-in for
     LibConvolve::new(sample_data) (audio_matcher.rs:289)."""
 
-    def __init__(self, sample_data, sr: int = 48000, config: Config | None = None, stream: int | None = None):
+    def __init__(self, sample_data, sr: int = 48000, config: Config | None = None, stream: int | None = None,
+                 batch: bool = False):
+        """`batch=True`: sample_data is a float32 array [n_snippets][m] matched as n independent snippets
+        that share the stream-side transforms (extension; the reference takes one snippet per run)."""
+        self.n_snippets = 1
+        if batch:
+            a = np.ascontiguousarray(sample_data, dtype=np.float32)
+            if a.ndim != 2 or a.shape[0] < 1 or a.shape[1] < 1:
+                raise ValueError("batch expects [n_snippets][m]")
+            self.sr, self.m, self.n_snippets = int(sr), int(a.shape[1]), int(a.shape[0])
+            self._config = config or Config()
+            cfg = self._config._native()
+            h = C.c_void_p()
+            N.check(N.lib().am_matcher_create_batch(a.ctypes.data, self.m, self.n_snippets, self.sr, C.byref(cfg), C.byref(h)))
+            self._h = h
+            if stream is not None:
+                self.set_stream(stream)
+            return
         ptr, frames, fmt, mem, keep = _describe(sample_data)
         if mem != N.MEM_HOST:
             raise TypeError("the snippet is taken from host memory (LibConvolve::new owns a copy)")
@@ -162,6 +179,9 @@ class CudaConvolve:
         s = N.AmStats()
         N.check(N.lib().am_matcher_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in N.AmStats._fields_}
+
+    def select_snippet(self, snippet_id: int) -> None:
+        N.check(N.lib().am_matcher_select_snippet(self._h, snippet_id))
 
     def set_profiling(self, on: bool) -> None:
         N.check(N.lib().am_matcher_set_profiling(self._h, int(on)))

@@ -25,11 +25,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (sr, channels, snippet_s, stream_hours per GPU, fft_log2)   -- BASELINE.json configs
-    "cfg1": (44100, 1, 10.0, 1.0, 22),
-    "cfg2": (48000, 1, 10.0, 24.0, 22),
-    "cfg4": (44100, 1, 30.0, 125.0, 23),
-    "cfg5": (96000, 2, 2.0, 12.5, 20),
+    # name: (sr, channels, snippet_s, stream_hours per GPU, fft_log2, n_snippets)   -- BASELINE.json configs
+    "cfg1": (44100, 1, 10.0, 1.0, 22, 1),
+    "cfg2": (48000, 1, 10.0, 24.0, 22, 1),
+    "cfg3": (48000, 1, 10.0, 24.0, 22, 64),
+    "cfg4": (44100, 1, 30.0, 125.0, 23, 1),
+    "cfg5": (96000, 2, 2.0, 12.5, 20, 1),
 }
 METRIC = "audio-hours matched/sec (snippet vs stream)"
 UNIT = "audio-hours/s"
@@ -98,7 +99,7 @@ def plant_plan(sr, snippet_s, total_frames):
     return out
 
 
-def run_reference(args, wl):
+def run_reference(args, wl, out_stream):
     """The reference algorithm's own CPU path (exact-length complex FFTs per 60 s chunk, snippet FFT
     recomputed per chunk, one worker thread per core), via the oracle port -- the Rust crate cannot be
     built in this image.  Each step is a bounded sample of the workload."""
@@ -106,7 +107,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     from oracle import am_oracle as orc
-    sr, ch, snip_s, hours, fft_log2 = wl
+    sr, ch, snip_s, hours, fft_log2, n_snip = wl
     cores = min(os.cpu_count() or 1, orc.threads(), 32)
     chunks = cores if args.sample_chunks <= 0 else args.sample_chunks
     stream_s = chunks * CHUNK_S
@@ -123,7 +124,7 @@ def run_reference(args, wl):
             times.append(dt)
         log(f"[reference] step {i}: {dt:.2f}s, {len(peaks)} peaks")
     total = sum(times)
-    value = (stream_s / 3600.0) * len(times) / total
+    value = (stream_s / 3600.0) * len(times) / total / n_snip     # a batch is n_snip independent reference runs
     sample = f"{chunks} logical chunks ({stream_s:.0f} s of {sr} Hz audio) of the {args.workload} workload per step, {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -132,16 +133,28 @@ def run_reference(args, wl):
         "config": {"workload": workload_name(args, wl), "note": "oracle port of the reference CPU path; Rust crate not buildable here"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }), file=out_stream, flush=True)
 
 
 def workload_name(args, wl):
-    sr, ch, snip_s, hours, fft_log2 = wl
-    return (f"{args.workload}: one {snip_s:g} s snippet vs {hours:g} h {sr} Hz {'stereo' if ch == 2 else 'mono'} int16 "
+    sr, ch, snip_s, hours, fft_log2, n_snip = wl
+    return (f"{args.workload}: {'one' if n_snip == 1 else n_snip} {snip_s:g} s snippet{'s' if n_snip > 1 else ''} vs {hours:g} h {sr} Hz {'stereo' if ch == 2 else 'mono'} int16 "
             f"stream per GPU, chunk 60 s, distance 480 s, prominence 0.13")
 
 
 def main():
+    # keep stdout clean for the single JSON line: libraries (NCCL's version banner, torchrun notices)
+    # write to fd 1 too, so everything else goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    try:
+        _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(out_stream):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -161,7 +174,7 @@ def main():
         wl[4] = args.fft_log2
     wl = tuple(wl)
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args, wl, out_stream)
         return
 
     import numpy as np
@@ -180,14 +193,18 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sr, ch, snip_s, hours, fft_log2 = wl
+    sr, ch, snip_s, hours, fft_log2, n_snip = wl
     m = int(round(snip_s * sr))
     frames_per_gpu = int(round(hours * 3600 * sr))
     total_frames = frames_per_gpu * world
     conf = am.Config(chunk_size=CHUNK_S, overlap_length=-1.0, peak_config=am.PeakConfig(DIST_S, PROM), fft_log2=fft_log2)
-    snip_np = orc.synth_pcm16(orc.SEED_SNIP, 0, m)
+    snips_np = [orc.synth_pcm16(orc.SEED_SNIP + i, 0, m) for i in range(n_snip)]
     stream = torch.cuda.current_stream()
-    algo = am.CudaConvolve(snip_np, sr=sr, config=conf, stream=stream.cuda_stream)
+    if n_snip == 1:
+        algo = am.CudaConvolve(snips_np[0], sr=sr, config=conf, stream=stream.cuda_stream)
+    else:
+        algo = am.CudaConvolve(np.stack([orc.pcm16_to_f32(x) for x in snips_np]), sr=sr, config=conf,
+                               stream=stream.cuda_stream, batch=True)
     total_chunks = algo.num_chunks(total_frames)
     c0, nc = shard_chunks(total_chunks, world, rank)
     lo, hi = shard_frames(c0, nc, total_frames, sr, conf, m)
@@ -196,16 +213,15 @@ def main():
     L = N.lib()
     pcm = torch.empty(((hi - lo), ch) if ch == 2 else (hi - lo,), dtype=torch.int16, device="cuda")
     N.check(L.am_synth_pcm16_device(orc.SEED_STREAM, lo * ch, (hi - lo) * ch, pcm.data_ptr(), stream.cuda_stream))
-    snip_dev = torch.from_numpy(snip_np).cuda()
+    snips_dev = [torch.from_numpy(x).cuda() for x in snips_np]
     plan = plant_plan(sr, snip_s, total_frames)
-    expected = set()
-    for o, shift in plan:
+    for k, (o, shift) in enumerate(plan):                  # occurrence k carries snippet k mod n_snip
         if o + m <= lo or o >= hi:
             continue
         skip = max(0, lo - o)
-        N.check(L.am_synth_plant_device(pcm.data_ptr(), hi - lo, ch, snip_dev.data_ptr() + 2 * skip, m - skip,
+        N.check(L.am_synth_plant_device(pcm.data_ptr(), hi - lo, ch, snips_dev[k % n_snip].data_ptr() + 2 * skip, m - skip,
                                         o + skip - lo, shift, stream.cuda_stream))
-    expected = {o for o, _ in plan}
+    expected = {(o, k % n_snip) for k, (o, _) in enumerate(plan)}
     torch.cuda.synchronize()
 
     def step(samples):
@@ -245,18 +261,19 @@ def main():
     ms_per_step = ms / args.steps
     value = (total_frames / sr / 3600.0) / (ms_per_step / 1000.0)
     # sanity: every reported offset is a planted one (the oracle parity proper lives in tests/)
-    starts = [p.position.start for p in peaks]
+    starts = [(p.position.start, p.snippet_id) for p in peaks]
     verified = len(starts) > 0 and all(s in expected for s in starts)
 
     # ---- roofline of the dominant kernel (algorithmic bytes, SURVEY.md 8d / DESIGN.md)
     n_fft = 1 << stats["fft_log2"] if stats["fft_log2"] else 0
     b_in = 2 * ch
     pairs = (stats["fft_blocks"] + 1) // 2
+    sigma = 1 if n_snip * 8 * n_fft > 100e6 else 0          # snippet spectra resident in L2 or not
     model_bytes = {
         "k_col_fwd": pairs * (2 * n_fft * b_in + 8 * n_fft),
-        "k_row": pairs * 16 * n_fft,
-        "k_col_inv": pairs * 8 * n_fft,
-        "k_small": pairs * 2 * n_fft * b_in,
+        "k_row": pairs * n_fft * (16 if n_snip == 1 else 16 + n_snip * (16 + 8 * sigma)),
+        "k_col_inv": pairs * 8 * n_fft * n_snip,
+        "k_small": pairs * 2 * n_fft * b_in * n_snip,
     }
     peak_gbs, peak_src = measured_hbm_peak()
     dom = max((k for k in ktimes if k in model_bytes), key=lambda k: ktimes[k]["total_ms"], default=None)
@@ -269,7 +286,7 @@ def main():
                     "launches_per_step": ktimes[dom]["launches"] / args.steps, "ms_per_step": per_step_ms,
                     "algorithmic_bytes_per_step": model_bytes[dom]}
     vn = n_fft - m + 1 if n_fft else 1
-    step_model_bytes = (hi - lo) * (b_in + 16) * n_fft / vn if n_fft else 0
+    step_model_bytes = (hi - lo) * (b_in + 8 + n_snip * (8 + 4 * sigma)) * n_fft / vn if n_fft else 0
     kernel_share = {k: round(v["total_ms"] / args.steps, 4) for k, v in ktimes.items()}
 
     # ---- end to end: PCM in pinned host memory, H2D inside the timed region
@@ -281,7 +298,7 @@ def main():
         e_ms, e_peaks = timed(host, min(args.warmup, 2), args.steps)
         est = algo.stats()
         e_value = (total_frames / sr / 3600.0) / (e_ms / args.steps / 1000.0)
-        verified = verified and [p.position.start for p in e_peaks] == starts
+        verified = verified and [(p.position.start, p.snippet_id) for p in e_peaks] == starts
         e2e = {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": est["h2d_bytes"], "d2h_bytes_per_step": est["d2h_bytes"],
                "ms_per_step": e_ms / args.steps}
         del host
@@ -313,6 +330,7 @@ def main():
         "config": {"workload": workload_name(args, wl), "fft_log2": stats["fft_log2"],
                    "four_step": f"{1 << stats['log2_n1']}x{1 << stats['log2_n2']}", "frames_per_gpu": hi - lo,
                    "l2_policy": "inputs larger than L2 (PCM per GPU %.1f GB)" % ((hi - lo) * b_in / 1e9),
+                   "n_snippets": n_snip, "snippet_hours_per_s": value * n_snip,
                    "peaks_found": len(starts), "planted": len(plan), "verified_offsets_are_planted": verified,
                    "model_bytes_per_step": step_model_bytes,
                    "model_gbs": step_model_bytes / (ms_per_step / 1000.0) / 1e9,
@@ -321,7 +339,7 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": stats["kernel_launches"] * args.steps,
         "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -113,6 +113,15 @@ am_status am_matcher_create(const float *snippet, size_t m, uint32_t sr, const a
 /* same from 16-bit PCM (channels 1 or 2), scaled/downmixed like mp3_reader.rs:35 */
 am_status am_matcher_create_pcm16(const int16_t *pcm, size_t frames, int channels, uint32_t sr,
                                   const am_config *cfg, am_matcher **out);
+/* Batch of n_snippets snippets of m samples each (row-major [n_snippets][m]) matched against the same
+ * stream: the stream-side transforms are shared, multiply + inverse + peak search run per snippet.
+ * The reference matches one snippet per run (src/matcher/mod.rs:29-34); results are defined as
+ * n_snippets independent runs, reported snippet-major with am_peak.snippet_id set. */
+am_status am_matcher_create_batch(const float *snippets, size_t m, size_t n_snippets, uint32_t sr,
+                                  const am_config *cfg, am_matcher **out);
+size_t am_matcher_snippet_count(const am_matcher *h);
+/* snippet used by am_correlate / am_inverse_sample_auto_correlation (default 0) */
+am_status am_matcher_select_snippet(am_matcher *h, size_t snippet_id);
 void am_matcher_destroy(am_matcher *h);
 
 /* run this matcher's work on a caller-owned cudaStream_t (NULL = the legacy default stream) */

@@ -154,6 +154,30 @@ def test_calc_chunks_random_vs_oracle(am, orc, seed, dist, prom, maxpk):
     _assert_peaks(got, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
 
 
+def test_batch_equals_independent_runs(am, orc):
+    """BASELINE config 3 semantics: a batch of snippets == one reference-semantics run per snippet."""
+    sr, m = 8000, 3000
+    pcm = orc.synth_pcm16(77, 0, sr * 41)
+    snips = [orc.synth_pcm16(500 + i, 0, m) for i in range(3)]
+    for k, o in enumerate([9000, 100123, 200500, 280000]):
+        orc.synth_plant(pcm, 1, snips[k % 3], o, k % 2)
+    conf = am.Config(chunk_size=5.0, peak_config=am.PeakConfig(2.0, 0.13), fft_log2=14)
+    batch = am.CudaConvolve(np.stack([orc.pcm16_to_f32(s) for s in snips]), sr=sr, config=conf, batch=True)
+    got = am.calc_chunks(sr, pcm, batch, True, conf)
+    assert batch.n_snippets == 3 and [p.snippet_id for p in got] == sorted(p.snippet_id for p in got)
+    x = orc.pcm16_to_f32(pcm)
+    for i, s in enumerate(snips):
+        sf = orc.pcm16_to_f32(s)
+        ref = orc.calc_chunks(x, sf, sr, orc.make_config(5.0, m / sr, 2.0, 0.13), scale=True, precision=64)
+        mine = [p for p in got if p.snippet_id == i]
+        assert len(ref) >= 1
+        _assert_peaks(mine, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+        batch.select_snippet(i)                                            # am_correlate on snippet i of the batch
+        c = batch.correlate_with_sample(x[:40000], am.Mode.Valid, True)
+        assert _rel(c, orc.correlate(x[:40000], sf, orc.MODE_VALID, 64) * orc.inv_autocorr(sf, exact=True)) < 5e-6
+    batch.close()
+
+
 def test_edge_cases(am, orc, native):
     sr = 8000
     snip = orc.synth_pcm16(7, 0, 4000)

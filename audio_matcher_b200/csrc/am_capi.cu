@@ -199,8 +199,11 @@ template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::Block
     static const int lt_env = [] { const char *v = getenv("AM_COL_LT"); return v && *v ? atoi(v) : 0; }();
     switch (l1) {
 #define C_(L) case L: return launch_col_t<L, amk::col_default_lt(L), INV>(h, g, l2, A);
-        C_(4) C_(5) C_(6) C_(7) C_(8) C_(11)
+        C_(4) C_(5) C_(6) C_(7) C_(11)
 #undef C_
+    case 8:
+        if (lt_env == 5) return launch_col_t<8, 5, INV>(h, g, l2, A);
+        return launch_col_t<8, 4, INV>(h, g, l2, A);
     case 9:                                   // tuning knob: tile of 8 or 16 columns
         if (lt_env == 3) return launch_col_t<9, 3, INV>(h, g, l2, A);
         return launch_col_t<9, 4, INV>(h, g, l2, A);
@@ -222,7 +225,7 @@ am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, 
 template <int MODE> am_status launch_row(am_matcher *h, int l2, float2 *A, const float2 *spec, float2 *B, int l1, int rows) {
     switch (l2) {
 #define C_(L) case L: return launch_row_t<L, MODE>(h, A, spec, B, l1, rows);
-        C_(10) C_(11) C_(12) C_(13)
+        C_(10) C_(11) C_(12) C_(13) C_(14)
 #undef C_
     }
     return fail(AM_ERR_UNSUPPORTED, "row length 2^%d not built", l2);
@@ -238,7 +241,7 @@ void split(int log2n, int &l1, int &l2) {
     const char *v = getenv("AM_ROW_LOG2");
     if (v && *v) {
         int x = atoi(v);
-        if (x >= 10 && x <= 13 && log2n - x >= 4 && log2n - x <= 11) l2 = x;
+        if (x >= 10 && x <= 14 && log2n - x >= 4 && log2n - x <= 11) l2 = x;
     }
     l1 = log2n - l2;
     if (l1 > 11) { l1 = 11; l2 = log2n - 11; }

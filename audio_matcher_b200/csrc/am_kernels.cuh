@@ -289,7 +289,7 @@ template <int L2> struct RowCfg {
     static constexpr int GT = N / EPT;
     static constexpr int THREADS = GT < 128 ? 128 : GT;
     static constexpr int G = THREADS / GT;
-    static constexpr int MINB = THREADS >= 512 ? 2 : 1024 / THREADS;
+    static constexpr int MINB = THREADS >= 1024 ? 1 : (THREADS >= 512 ? 2 : 1024 / THREADS);
     static constexpr size_t SMEM = (size_t)G * RegFFT<L2, 0, false>::SMEM_ELEMS * sizeof(float2);
 };
 
@@ -354,6 +354,7 @@ k_row(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restric
         }
     }
 }
+
 
 // sum of squares of the snippet in double (inverse_sample_auto_correlation, audio_matcher.rs:321-329)
 __global__ void k_sumsq(StreamView sv, long long m, double *out) {

@@ -217,6 +217,12 @@ class CudaConvolve:
 
     def _calc(self, samples, scale: bool, total_frames: int | None, buf_first_frame: int, first_chunk: int,
               num_chunks: int | None, final_filter: bool, cap: int) -> list[Peak]:
+        buf, n = self._calc_raw(samples, scale, total_frames, buf_first_frame, first_chunk, num_chunks, final_filter, cap)
+        return [Peak._from_native(buf[i]) for i in range(n)]
+
+    def _calc_raw(self, samples, scale: bool, total_frames: int | None, buf_first_frame: int, first_chunk: int,
+                  num_chunks: int | None, final_filter: bool, cap: int):
+        """-> (ctypes array of am_peak, count): the C-ABI call without building Python objects."""
         ptr, frames, fmt, mem, keep = _describe(samples)
         total = frames if total_frames is None else int(total_frames)
         buf = (N.AmPeak * cap)()
@@ -224,7 +230,7 @@ class CudaConvolve:
         nc = (1 << 62) if num_chunks is None else int(num_chunks)
         N.check(N.lib().am_calc_chunks_range(self._h, ptr, buf_first_frame, frames, total, fmt, mem, int(bool(scale)),
                                              first_chunk, nc, int(final_filter), buf, cap, C.byref(got)))
-        return [Peak._from_native(buf[i]) for i in range(got.value)]
+        return buf, got.value
 
 
 def calc_chunks(sr: int, m_samples, algo_with_sample: CudaConvolve, scale: bool, config: Config,
@@ -272,51 +278,69 @@ def shard_frames(first_chunk: int, num_chunks: int, total_frames: int, sr: int, 
     return lo, hi
 
 
-def gather_peaks(local: Sequence[Peak], group=None) -> list[Peak]:
-    """All-gather of the per-rank candidate lists (KB-sized) through torch.distributed (NCCL on
-    GPUs, gloo in the CPU tests)."""
+def _pack(peaks: Sequence[Peak]):
+    arr = (N.AmPeak * max(len(peaks), 1))(*[p._native() for p in peaks])
+    return arr, len(peaks)
+
+
+def gather_raw(arr, count: int, group=None, cap: int = 4096):
+    """All-gather of per-rank am_peak arrays (KB-sized) through torch.distributed: NCCL between GPUs,
+    gloo in the CPU tests.  One collective: every rank contributes a fixed-size record
+    [count:int64][cap * sizeof(am_peak) bytes]; a second round only if some rank overflows `cap`."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return list(local)
+        return arr, count
     ws = dist.get_world_size(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    rows = np.zeros((len(local), 4), dtype=np.int64)
-    for i, p in enumerate(local):
-        f = np.array([p.height, p.prominence, p.left_diff, p.right_diff], dtype=np.float32).view(np.int32).astype(np.int64)
-        rows[i, 0] = p.position.start
-        rows[i, 1] = p.position.stop
-        rows[i, 2] = (f[0] & 0xFFFFFFFF) | ((f[1] & 0xFFFFFFFF) << 32)
-        rows[i, 3] = (f[2] & 0xFFFFFFFF) | ((f[3] & 0xFFFFFFFF) << 32)
-    chunk_ids = np.array([p.chunk for p in local], dtype=np.int64)
-    count = torch.tensor([len(local)], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(count) for _ in range(ws)]
-    dist.all_gather(counts, count, group=group)
-    mx = max(int(c.item()) for c in counts)
-    payload = torch.zeros((max(mx, 1), 5), dtype=torch.int64, device=dev)
-    if len(local):
-        payload[:len(local), :4] = torch.from_numpy(rows).to(dev)
-        payload[:len(local), 4] = torch.from_numpy(chunk_ids).to(dev)
-    gathered = [torch.zeros_like(payload) for _ in range(ws)]
-    dist.all_gather(gathered, payload, group=group)
-    out: list[Peak] = []
+    psz = C.sizeof(N.AmPeak)
+    while True:
+        rec = np.zeros(8 + cap * psz, dtype=np.uint8)
+        rec[:8] = np.frombuffer(np.int64(count).tobytes(), dtype=np.uint8)
+        n_here = min(count, cap)
+        if n_here:
+            rec[8:8 + n_here * psz] = np.frombuffer(arr, dtype=np.uint8, count=n_here * psz)
+        mine = torch.from_numpy(rec).to(dev)
+        out = torch.empty(ws * rec.size, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, mine, group=group)
+        host = out.cpu().numpy().reshape(ws, rec.size)
+        counts = [int(np.frombuffer(host[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(ws)]
+        if max(counts) <= cap:
+            break
+        cap = max(counts)                                   # rare: somebody had more candidates than the record holds
+    total = sum(counts)
+    merged = (N.AmPeak * max(total, 1))()
+    off = 0
     for r in range(ws):
-        g = gathered[r][:int(counts[r].item())].cpu().numpy()
-        for row in g:
-            f = np.array([row[2] & 0xFFFFFFFF, (row[2] >> 32) & 0xFFFFFFFF, row[3] & 0xFFFFFFFF,
-                          (row[3] >> 32) & 0xFFFFFFFF], dtype=np.uint32).view(np.float32)
-            out.append(Peak(range(int(row[0]), int(row[1])), float(f[0]), float(f[1]), float(f[2]), float(f[3]),
-                            int(row[4])))
-    return out
+        nb = counts[r] * psz
+        if nb:
+            C.memmove(C.addressof(merged) + off, host[r, 8:8 + nb].ctypes.data, nb)
+            off += nb
+    return merged, total
+
+
+def gather_peaks(local: Sequence[Peak], group=None) -> list[Peak]:
+    arr, n = _pack(local)
+    arr, n = gather_raw(arr, n, group)
+    return [Peak._from_native(arr[i]) for i in range(n)]
+
+
+def _merge_raw(arr, n: int, sr: int, distance: float) -> list[Peak]:
+    dst = (N.AmPeak * max(n, 1))()
+    got = C.c_size_t()
+    N.check(N.lib().am_merge_peaks(arr, n, sr, distance, dst, n, C.byref(got)))
+    return [Peak._from_native(dst[i]) for i in range(got.value)]
 
 
 def calc_chunks_sharded(sr: int, shard_samples, algo_with_sample: CudaConvolve, scale: bool, config: Config, *,
                         total_frames: int, buf_first_frame: int, first_chunk: int, num_chunks: int, group=None,
-                        cap: int = 1 << 16) -> list[Peak]:
+                        cap: int = 1 << 16, set_config: bool = True) -> list[Peak]:
     """Multi-GPU calc_chunks: this rank runs logical chunks [first_chunk, first_chunk + num_chunks) on
     the frames it holds (its range plus the overlap halo, no halo exchange), the per-rank candidates
     are all-gathered, and every rank applies the global sort + neighbour filter."""
-    algo_with_sample.set_config(config)
-    local = algo_with_sample._calc(shard_samples, scale, total_frames, buf_first_frame, first_chunk, num_chunks,
-                                   False, cap)
-    return merge_peaks(gather_peaks(local, group), sr, config.peak_config.distance)
+    if set_config:
+        algo_with_sample.set_config(config)
+    arr, n = algo_with_sample._calc_raw(shard_samples, scale, total_frames, buf_first_frame, first_chunk, num_chunks,
+                                        False, cap)
+    arr, n = gather_raw(arr, n, group)
+    return _merge_raw(arr, n, sr, config.peak_config.distance)

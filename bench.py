@@ -35,6 +35,10 @@ WORKLOADS = {
 METRIC = "audio-hours matched/sec (snippet vs stream)"
 UNIT = "audio-hours/s"
 CHUNK_S, DIST_S, PROM = 60.0, 480.0, 0.13
+# dram__bytes_read.sum + dram__bytes_write.sum per block pair at N = 2^22, from the ncu --set full capture
+# summarised in profiles/r01_ncu_full_final.csv (5-pair launches: k_row 254.7 + 123.5 MB, k_col_fwd 68.4 + 114.6 MB,
+# k_col_inv 168.7 + 86.6 MB)
+NCU_DRAM_BYTES_PER_PAIR_2P22 = {"k_row": 75.6e6, "k_col_fwd": 36.6e6, "k_col_inv": 51.1e6}
 PLANT_PERIOD_S, PLANT_JITTER_S = 600.0, 30.0
 
 
@@ -183,7 +187,7 @@ def _main(out_stream):
     import ctypes as C
     import audio_matcher_b200 as am
     from audio_matcher_b200 import _native as N
-    from audio_matcher_b200.matcher import shard_chunks, shard_frames, gather_peaks, merge_peaks
+    from audio_matcher_b200.matcher import shard_chunks, shard_frames, calc_chunks_sharded
     from oracle import am_oracle as orc   # workload constants + CPU baseline only
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,8 +231,8 @@ def _main(out_stream):
     def step(samples):
         if world == 1:
             return algo._calc(samples, True, total_frames, lo, c0, nc, True, 1 << 16)
-        local = algo._calc(samples, True, total_frames, lo, c0, nc, False, 1 << 16)
-        return merge_peaks(gather_peaks(local), sr, DIST_S)
+        return calc_chunks_sharded(sr, samples, algo, True, conf, total_frames=total_frames, buf_first_frame=lo,
+                                   first_chunk=c0, num_chunks=nc, cap=1 << 14, set_config=False)
 
     def timed(samples, warmup, steps, profile=False):
         for _ in range(warmup):
@@ -281,8 +285,14 @@ def _main(out_stream):
     if dom:
         per_step_ms = ktimes[dom]["total_ms"] / args.steps
         achieved = model_bytes[dom] / (per_step_ms / 1000.0) / 1e9
+        traffic = None
+        if stats["fft_log2"] == 22 and n_snip == 1 and dom in NCU_DRAM_BYTES_PER_PAIR_2P22:
+            traffic = NCU_DRAM_BYTES_PER_PAIR_2P22[dom] * pairs / (ktimes[dom]["launches"] / args.steps)   # per launch
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                    "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak_gbs, "traffic": traffic,
+                    "traffic_source": "ncu dram bytes per block pair (profiles/r01_ncu_full_final.csv) x pairs per launch",
+                    "algorithmic_bytes_per_launch": model_bytes[dom] / (ktimes[dom]["launches"] / args.steps),
+                    "peak_source": peak_src,
                     "launches_per_step": ktimes[dom]["launches"] / args.steps, "ms_per_step": per_step_ms,
                     "algorithmic_bytes_per_step": model_bytes[dom]}
     vn = n_fft - m + 1 if n_fft else 1

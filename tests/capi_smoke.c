@@ -1,0 +1,55 @@
+/* capi_smoke.c -- the C ABI used from plain C (no Python, no C++): what a cgo/FFI caller sees.
+ * Built and run by tests/test_gpu_parity.py::test_c_abi_from_plain_c.
+ *   gcc -std=c11 -I include tests/capi_smoke.c -L audio_matcher_b200 -laudio_matcher_b200 -lm
+ * Reference KAT: src/matcher/audio_matcher.rs:489-517 (Valid, unscaled, [-10,10) vs [1,2,3]). */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include "audio_matcher.h"
+
+int main(void) {
+    if (am_abi_version() != AM_ABI_VERSION) { fprintf(stderr, "ABI version mismatch\n"); return 2; }
+    if (am_device_count() < 1) { fprintf(stderr, "no CUDA device: %s\n", "cannot run"); return 77; }
+    float snippet[3] = {1.f, 2.f, 3.f}, within[20], out[32];
+    for (int i = 0; i < 20; ++i) within[i] = (float)(i - 10);
+    am_config cfg;
+    am_config_default(&cfg);
+    am_matcher *h = NULL;
+    if (am_matcher_create(snippet, 3, 1, &cfg, &h) != AM_OK) { fprintf(stderr, "create: %s\n", am_last_error()); return 1; }
+    size_t n = 0;
+    if (am_correlate(h, within, 20, AM_FMT_F32_MONO, AM_MEM_HOST, AM_MODE_VALID, 0, out, 32, AM_MEM_HOST, &n) != AM_OK) {
+        fprintf(stderr, "correlate: %s\n", am_last_error());
+        return 1;
+    }
+    if (n != 18) { fprintf(stderr, "expected 18 outputs, got %zu\n", n); return 1; }
+    for (size_t k = 0; k < n; ++k)
+        if (fabsf(out[k] - (float)(-52 + 6 * (int)k)) > 1.2e-5f) { fprintf(stderr, "out[%zu] = %g\n", k, out[k]); return 1; }
+    float inv = 0.f;
+    am_inverse_sample_auto_correlation(h, &inv);
+    if (fabsf(inv - 1.0f / 14.0f) > 1e-8f) { fprintf(stderr, "inverse autocorrelation %g\n", inv); return 1; }
+    /* error path: capacity too small must fail loudly, not truncate */
+    if (am_correlate(h, within, 20, AM_FMT_F32_MONO, AM_MEM_HOST, AM_MODE_VALID, 0, out, 4, AM_MEM_HOST, &n) != AM_ERR_CAPACITY) {
+        fprintf(stderr, "capacity error not reported\n");
+        return 1;
+    }
+    /* calc_chunks through the ABI: 1-tap snippet, the find_peaks KAT of audio_matcher.rs:167-185 */
+    float one = 1.f, y[7] = {0.f, 0.7f, 0.5f, 1.0f, 0.5f, 0.8f, 0.f};
+    am_matcher *g = NULL;
+    cfg.chunk_size_s = 7.0; cfg.overlap_s = 0.0; cfg.distance_s = 0.0; cfg.prominence = 0.0f;
+    if (am_matcher_create(&one, 1, 1, &cfg, &g) != AM_OK) { fprintf(stderr, "create: %s\n", am_last_error()); return 1; }
+    am_peak peaks[8];
+    if (am_calc_chunks(g, y, 7, AM_FMT_F32_MONO, AM_MEM_HOST, 1, peaks, 8, &n) != AM_OK) {
+        fprintf(stderr, "calc_chunks: %s\n", am_last_error());
+        return 1;
+    }
+    if (n != 3 || peaks[0].start != 1 || peaks[1].start != 3 || peaks[2].start != 5 ||
+        fabsf(peaks[1].prominence - 1.0f) > 1e-6f || fabsf(peaks[2].prominence - 0.3f) > 1e-6f ||
+        fabsf(peaks[0].prominence - 0.2f) > 1e-6f) {
+        fprintf(stderr, "find_peaks KAT failed (%zu peaks)\n", n);
+        return 1;
+    }
+    am_matcher_destroy(g);
+    am_matcher_destroy(h);
+    printf("capi_smoke ok\n");
+    return 0;
+}

@@ -305,6 +305,18 @@ def test_host_memory_path_equals_device_path(am, orc, full_size):
     assert st["h2d_bytes"] >= frames * 2 and len(a) > 0
 
 
+def test_c_abi_from_plain_c(am, native, tmp_path):
+    """The boundary is a C ABI: compile tests/capi_smoke.c with gcc against include/ and the .so, run it."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "capi_smoke"
+    libdir = os.path.join(root, "audio_matcher_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c11", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "capi_smoke.c"),
+                    "-L", libdir, "-laudio_matcher_b200", "-lm", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "capi_smoke ok" in out.stdout, out.stderr
+
+
 def test_two_gpu_sharded_nccl(am):
     import torch
     if torch.cuda.device_count() < 2:

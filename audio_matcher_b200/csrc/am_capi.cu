@@ -182,34 +182,37 @@ am_status launch_small(am_matcher *h, int log2n, const amk::BlockGroup &g, const
     return fail(AM_ERR_UNSUPPORTED, "single-pass length 2^%d not built", log2n);
 }
 
-template <int L1, int LT, bool INV> am_status launch_col_t(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *A) {
-    typedef amk::ColCfg<L1, LT> Cfg;
+template <int L1, int LT, int E, bool INV> am_status launch_col_t(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *A) {
+    typedef amk::ColCfg<L1, LT, E> Cfg;
     int pairs = (g.nblocks + 1) / 2;
     dim3 grid((1u << l2) >> Cfg::LT, pairs);
     if (INV) {
-        TRY(set_smem(amk::k_col_inv<L1, LT>, Cfg::SMEM));
-        LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
+        TRY(set_smem(amk::k_col_inv<L1, LT, E>, Cfg::SMEM));
+        LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT, E><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
     } else {
-        TRY(set_smem(amk::k_col_fwd<L1, LT>, Cfg::SMEM));
-        LAUNCH(h, AM_K_COL_FWD, amk::k_col_fwd<L1, LT><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
+        TRY(set_smem(amk::k_col_fwd<L1, LT, E>, Cfg::SMEM));
+        LAUNCH(h, AM_K_COL_FWD, amk::k_col_fwd<L1, LT, E><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
     }
     return AM_OK;
 }
 template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::BlockGroup &g, int l2, float2 *A) {
     static const int lt_env = [] { const char *v = getenv("AM_COL_LT"); return v && *v ? atoi(v) : 0; }();
+    static const int ept = [] { const char *v = getenv("AM_COL_EPT"); return v && *v ? atoi(v) : 32; }();
     switch (l1) {
-#define C_(L) case L: return launch_col_t<L, amk::col_default_lt(L), INV>(h, g, l2, A);
+#define C_(L) case L: return launch_col_t<L, amk::col_default_lt(L), 16, INV>(h, g, l2, A);
         C_(4) C_(5) C_(6) C_(7) C_(11)
 #undef C_
     case 8:
-        if (lt_env == 5) return launch_col_t<8, 5, INV>(h, g, l2, A);
-        return launch_col_t<8, 4, INV>(h, g, l2, A);
-    case 9:                                   // tuning knob: tile of 8 or 16 columns
-        if (lt_env == 3) return launch_col_t<9, 3, INV>(h, g, l2, A);
-        return launch_col_t<9, 4, INV>(h, g, l2, A);
+        if (lt_env == 5) return launch_col_t<8, 5, 16, INV>(h, g, l2, A);
+        return launch_col_t<8, 4, 16, INV>(h, g, l2, A);
+    case 9:                                   // tuning knobs: 8 or 16 columns per tile, 16 or 32 elements per thread
+        if (ept == 32) return launch_col_t<9, 4, 32, INV>(h, g, l2, A);
+        if (lt_env == 3) return launch_col_t<9, 3, 16, INV>(h, g, l2, A);
+        return launch_col_t<9, 4, 16, INV>(h, g, l2, A);
     case 10:
-        if (lt_env == 4) return launch_col_t<10, 4, INV>(h, g, l2, A);
-        return launch_col_t<10, 3, INV>(h, g, l2, A);
+        if (ept == 32) return launch_col_t<10, 4, 32, INV>(h, g, l2, A);
+        if (lt_env == 4) return launch_col_t<10, 4, 16, INV>(h, g, l2, A);
+        return launch_col_t<10, 3, 16, INV>(h, g, l2, A);
     }
     return fail(AM_ERR_UNSUPPORTED, "column length 2^%d not built", l1);
 }
@@ -217,6 +220,15 @@ template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::Block
 template <int L2, int MODE>
 am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, int l1, int rows) {
     typedef amk::RowCfg<L2> Cfg;
+    static const int ept = [] { const char *v = getenv("AM_ROW_EPT"); return v && *v ? atoi(v) : 32; }();
+    if constexpr (MODE == amk::ROW_FUSED && L2 == 13) {
+        if (ept == 32) {
+            typedef amk::Row32Cfg<L2> C32;
+            TRY(set_smem(amk::k_row32<L2>, C32::SMEM));
+            LAUNCH(h, AM_K_ROW, amk::k_row32<L2><<<rows, C32::THREADS, C32::SMEM, h->stream>>>(A, spec, l1, rows, h->d_tw.p));
+            return AM_OK;
+        }
+    }
     TRY(set_smem(amk::k_row<L2, MODE>, Cfg::SMEM));
     int grid = (rows + Cfg::G - 1) / Cfg::G;
     LAUNCH(h, AM_K_ROW, amk::k_row<L2, MODE><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(A, spec, B, l1, rows, h->d_tw.p));

@@ -96,11 +96,35 @@ template <bool INV> AM_HD void dft16(float2 *v) {
     AM_SWAP(1, 4) AM_SWAP(2, 8) AM_SWAP(3, 12) AM_SWAP(6, 9) AM_SWAP(7, 13) AM_SWAP(11, 14)
 #undef AM_SWAP
 }
+// 32 = 2 x 16: even / odd halves through dft16, W32^k on the odd half, radix-2 combine
+template <bool INV> AM_HD void dft32(float2 *v) {
+    float2 e[16], o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    dft16<INV>(e);
+    dft16<INV>(o);
+    // cos / sin of pi k / 16, k = 0..15
+    constexpr float C[16] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                             0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f,
+                             0.f, -0.19509032201612826785f, -0.38268343236508977173f, -0.55557023301960222474f,
+                             -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128675613f, -0.98078528040323044913f};
+    constexpr float S[16] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                             0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f,
+                             1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                             0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        float2 t = (k == 0) ? o[0] : (k == 8 ? mul_mi<INV>(o[8]) : mul_w<INV>(o[k], C[k], S[k]));
+        v[k] = cadd(e[k], t);
+        v[k + 16] = csub(e[k], t);
+    }
+}
 template <int R, bool INV> AM_HD void dft(float2 *v) {
     if constexpr (R == 2) dft2<INV>(v[0], v[1]);
     else if constexpr (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
     else if constexpr (R == 8) dft8<INV>(v);
-    else dft16<INV>(v);
+    else if constexpr (R == 16) dft16<INV>(v);
+    else dft32<INV>(v);
 }
 
 // v[r] *= w^r, r = 1..R-1, with w^r built by a depth-log2(R) product tree
@@ -120,6 +144,16 @@ template <int R> AM_HD void apply_twiddle_powers(float2 *v, float2 w1) {
                 v[11] = cmul(v[11], cmul(w8, w3)); v[12] = cmul(v[12], cmul(w8, w4));
                 v[13] = cmul(v[13], cmul(w8, w5)); v[14] = cmul(v[14], cmul(w8, w6));
                 v[15] = cmul(v[15], cmul(w8, w7));
+                if constexpr (R >= 32) {
+                    const float2 w16 = cmul(w8, w8);
+                    const float2 lo[8] = {make_float2(1.f, 0.f), w1, w2, w3, w4, w5, w6, w7};
+                    v[16] = cmul(v[16], w16);
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) v[16 + i] = cmul(v[16 + i], cmul(w16, lo[i]));
+                    const float2 w24 = cmul(w16, w8);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[24 + i] = cmul(v[24 + i], i ? cmul(w24, lo[i]) : w24);
+                }
             }
         }
     }
@@ -127,11 +161,15 @@ template <int R> AM_HD void apply_twiddle_powers(float2 *v, float2 w1) {
 
 // Transform plan: LOG2N = length, LOG2B = batch (columns interleaved), INV = direction.
 // GT = threads in the group that owns the N*B elements (N*B == 16*GT).
-template <int LOG2N, int LOG2B, bool INV> struct RegFFT {
+// E = complex elements per thread (16, or 32 for long rows: radix-32 first stage, one exchange fewer).
+template <int LOG2N, int LOG2B, bool INV, int E = EPT> struct RegFFT {
     static constexpr int N = 1 << LOG2N, B = 1 << LOG2B;
+    static constexpr int EPT = E;                    // shadows amfft::EPT inside the plan
+    static constexpr int MAXB = (E == 32) ? 5 : 4;   // largest radix = E
     static constexpr int GT = (N * B) / EPT;
-    static constexpr int NST = (LOG2N + 3) / 4;
-    static_assert(LOG2N >= 4 && LOG2N <= TW_LOG2, "unsupported length");
+    static constexpr int NST = (LOG2N + MAXB - 1) / MAXB;
+    static_assert(E == 16 || E == 32, "16 or 32 elements per thread");
+    static_assert(LOG2N >= MAXB && LOG2N <= TW_LOG2, "unsupported length");
     static_assert(N * B >= EPT, "group too small");
     // radix bits of stage st in execution order (inverse = forward plan reversed)
     static constexpr int bits_at(int st) {

@@ -163,12 +163,15 @@ k_small(BlockGroup g, const float2 *__restrict__ spec, const float2 *__restrict_
 // ---- four-step path ---------------------------------------------------------------
 // default tile width (log2 columns): N1*T >= 2048 elements and <= 64 KB of exchange buffer
 constexpr int col_default_lt(int l1) { return l1 >= 10 ? 13 - l1 : (l1 >= 7 ? 4 : 11 - l1); }
-template <int L1, int LT_ = col_default_lt(L1)> struct ColCfg {
+template <int L1, int LT_ = col_default_lt(L1), int E_ = 16> struct ColCfg {
+    static constexpr int E = E_;
     static constexpr int LT = LT_;
     static constexpr int T = 1 << LT;
-    static constexpr int THREADS = ((1 << L1) * T) / EPT;
-    static constexpr int MINB = THREADS >= 1024 ? 1 : 1024 / THREADS;   // <= 64 registers
-    static constexpr size_t SMEM = (size_t)RegFFT<L1, LT, false>::SMEM_ELEMS * sizeof(float2);
+    static constexpr int THREADS = ((1 << L1) * T) / E;
+    static constexpr int MINB = THREADS >= 1024 ? 1 : (1024 * 16 / E) / THREADS;   // <= 64 (E = 16) / 128 (E = 32) registers
+    // the inverse kernel fits 80 registers without spilling: a third resident CTA hides more load latency
+    static constexpr int MINB_INV = (E == 32 && THREADS == 256) ? 3 : MINB;
+    static constexpr size_t SMEM = (size_t)RegFFT<L1, LT, false, E>::SMEM_ELEMS * sizeof(float2);
 };
 
 // exp(-+ 2 pi i p / N), p < N <= 2^24 (p and 2/N exact in fp32)
@@ -196,10 +199,10 @@ template <int R> __device__ __forceinline__ void twiddle_geo(float2 *v, float2 b
 }
 
 template <int FMT, class F, int LT>
-__device__ __forceinline__ void load_tile_fast(float2 (&v)[EPT], const BlockGroup &g, long long v0, int log2n2, int n2_0, int tid) {
+__device__ __forceinline__ void load_tile_fast(float2 (&v)[F::EPT], const BlockGroup &g, long long v0, int log2n2, int n2_0, int tid) {
     const long long f0 = v0 - g.sv.lead - g.sv.buf_first;
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) {
+    for (int j = 0; j < F::EPT; ++j) {
         int idx, t;
         F::template in_coord<0>(tid, j, idx, t);
         long long f = f0 + ((long long)idx << log2n2) + n2_0 + t;
@@ -208,11 +211,12 @@ __device__ __forceinline__ void load_tile_fast(float2 (&v)[EPT], const BlockGrou
 }
 
 // grid (N2 / T, pairs).  A[pair][k1][n2] = W_N^{n2 k1} * sum_{n1} z[n1 N2 + n2] W_N1^{n1 k1}
-template <int L1, int LT>
-__global__ void __launch_bounds__(ColCfg<L1, LT>::THREADS, ColCfg<L1, LT>::MINB)
+template <int L1, int LT, int E>
+__global__ void __launch_bounds__(ColCfg<L1, LT, E>::THREADS, ColCfg<L1, LT, E>::MINB)
 k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__restrict__ tw) {
-    typedef ColCfg<L1, LT> Cfg;
-    typedef RegFFT<L1, Cfg::LT, false> F;
+    typedef ColCfg<L1, LT, E> Cfg;
+    typedef RegFFT<L1, Cfg::LT, false, E> F;
+    constexpr int EPT = E;
     extern __shared__ float2 sm_all[];
     const int tid = threadIdx.x, pair = blockIdx.y;
     const int n2_0 = blockIdx.x << Cfg::LT;
@@ -263,11 +267,12 @@ k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__rest
 }
 
 // grid (N2 / T, pairs).  y[n1 N2 + n2] = sum_{k1} W_N1^{-n1 k1} W_N^{-n2 k1} B[k1][n2]
-template <int L1, int LT>
-__global__ void __launch_bounds__(ColCfg<L1, LT>::THREADS, ColCfg<L1, LT>::MINB)
+template <int L1, int LT, int E>
+__global__ void __launch_bounds__(ColCfg<L1, LT, E>::THREADS, ColCfg<L1, LT, E>::MINB_INV)
 k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *__restrict__ tw) {
-    typedef ColCfg<L1, LT> Cfg;
-    typedef RegFFT<L1, Cfg::LT, true> I;
+    typedef ColCfg<L1, LT, E> Cfg;
+    typedef RegFFT<L1, Cfg::LT, true, E> I;
+    constexpr int EPT = E;
     extern __shared__ float2 sm_all[];
     const int tid = threadIdx.x, pair = blockIdx.y;
     const int n2_0 = blockIdx.x << Cfg::LT;
@@ -400,6 +405,49 @@ k_row(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restric
     }
 }
 
+
+
+// Fused row kernel with 32 elements per thread: radix 32-16-16 for 8192 points, i.e. TWO exchanges per
+// transform instead of three.  k_row is bound by the shared-memory pipe (768 KB of exchange traffic per
+// row at 128 B/clk) and FP issue, so a third less exchange traffic and one twiddled stage less is what
+// this variant buys; it pays with 128 registers per thread (256 threads per row, 2 CTAs per SM).
+template <int L2> struct Row32Cfg {
+    static constexpr int THREADS = (1 << L2) / 32;
+    static constexpr size_t SMEM = (size_t)RegFFT<L2, 0, false, 32>::SMEM_ELEMS * sizeof(float2);
+};
+template <int L2>
+__global__ void __launch_bounds__(Row32Cfg<L2>::THREADS, 2)
+k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, int log2n1, int rows, const float2 *__restrict__ tw) {
+    typedef RegFFT<L2, 0, false, 32> F;
+    typedef RegFFT<L2, 0, true, 32> I;
+    extern __shared__ float2 sm[];
+    const int gtid = threadIdx.x;
+    const int row = blockIdx.x;
+    float2 *Ar = A + ((size_t)row << L2);
+    float2 v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        int idx, t;
+        F::template in_coord<0>(gtid, j, idx, t);
+        v[j] = Ar[idx];
+    }
+    F::run(v, sm, gtid, tw);
+    const float2 *Sr = spec + ((size_t)(row & ((1 << log2n1) - 1)) << L2);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        int idx, t;
+        I::template in_coord<0>(gtid, j, idx, t);
+        v[j] = amfft::cmul(v[j], __ldg(&Sr[idx]));
+    }
+    __syncthreads();
+    I::run(v, sm, gtid, tw);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        int idx, t;
+        I::out_coord(gtid, j, idx, t);
+        Ar[idx] = v[j];
+    }
+}
 
 // sum of squares of the snippet in double (inverse_sample_auto_correlation, audio_matcher.rs:321-329)
 __global__ void k_sumsq(StreamView sv, long long m, double *out) {

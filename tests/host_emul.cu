@@ -31,6 +31,7 @@ static void ref_fft(std::vector<cd> &a, bool inv) {   // recursive radix-2, doub
 static std::vector<float2> g_tw;
 
 template <class F, int ST> struct Runner {
+    static constexpr int EPT = F::EPT;
     static void go(std::vector<float2> &regs, std::vector<float2> &sm) {
         constexpr int GT = F::GT;
         for (int t = 0; t < GT; ++t) F::template butterfly<ST>(*(float2(*)[EPT]) & regs[t * EPT], t, g_tw.data());
@@ -42,9 +43,9 @@ template <class F, int ST> struct Runner {
     }
 };
 
-template <int LOG2N, int LOG2B, bool INV> static double check() {
-    typedef RegFFT<LOG2N, LOG2B, INV> F;
-    constexpr int N = F::N, B = F::B, GT = F::GT;
+template <int LOG2N, int LOG2B, bool INV, int E = 16> static double check() {
+    typedef RegFFT<LOG2N, LOG2B, INV, E> F;
+    constexpr int N = F::N, B = F::B, GT = F::GT, EPT = E;
     std::vector<float2> x(N * B);
     srand(1234 + LOG2N * 31 + LOG2B);
     for (auto &e : x) e = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
@@ -75,17 +76,17 @@ template <int LOG2N, int LOG2B, bool INV> static double check() {
         }
     }
     double rel = maxerr / maxref;
-    printf("fft log2n=%d log2b=%d inv=%d stages=%d  max_rel_err=%.3g %s\n", LOG2N, LOG2B, (int)INV, F::NST, rel,
+    printf("fft log2n=%d log2b=%d inv=%d ept=%d stages=%d  max_rel_err=%.3g %s\n", LOG2N, LOG2B, (int)INV, E, F::NST, rel,
            rel < 2e-6 ? "OK" : "FAIL");
     return rel;
 }
 
 // the forward-then-inverse register hand-over used by the row kernel: after the forward
 // transform the thread multiplies its registers and feeds them to the inverse unchanged.
-template <int LOG2N> static double check_roundtrip() {
-    typedef RegFFT<LOG2N, 0, false> F;
-    typedef RegFFT<LOG2N, 0, true> I;
-    constexpr int N = F::N, GT = F::GT;
+template <int LOG2N, int E = 16> static double check_roundtrip() {
+    typedef RegFFT<LOG2N, 0, false, E> F;
+    typedef RegFFT<LOG2N, 0, true, E> I;
+    constexpr int N = F::N, GT = F::GT, EPT = E;
     std::vector<float2> x(N);
     for (auto &e : x) e = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
     std::vector<float2> regs(GT * EPT), sm(F::SMEM_ELEMS);
@@ -129,6 +130,12 @@ int main() {
     worst = std::max(worst, check_roundtrip<4>());
     worst = std::max(worst, check_roundtrip<9>());
     worst = std::max(worst, check_roundtrip<13>());
+#define CHK32(n) worst = std::max(worst, check<n, 0, false, 32>()); worst = std::max(worst, check<n, 0, true, 32>());
+    CHK32(5) CHK32(9) CHK32(10) CHK32(13) CHK32(14)
+    worst = std::max(worst, check<9, 4, false, 32>()); worst = std::max(worst, check<9, 4, true, 32>());
+    worst = std::max(worst, check<10, 4, false, 32>()); worst = std::max(worst, check<10, 4, true, 32>());
+    worst = std::max(worst, check_roundtrip<13, 32>());
+    worst = std::max(worst, check_roundtrip<14, 32>());
     printf(worst < 2e-6 ? "ALL OK\n" : "SOME FAILED\n");
     return worst < 2e-6 ? 0 : 1;
 }

@@ -221,11 +221,11 @@ template <int L2, int MODE>
 am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, int l1, int rows) {
     typedef amk::RowCfg<L2> Cfg;
     static const int ept = [] { const char *v = getenv("AM_ROW_EPT"); return v && *v ? atoi(v) : 32; }();
-    if constexpr (MODE == amk::ROW_FUSED && L2 == 13) {
+    if constexpr (L2 == 13) {
         if (ept == 32) {
             typedef amk::Row32Cfg<L2> C32;
-            TRY(set_smem(amk::k_row32<L2>, C32::SMEM));
-            LAUNCH(h, AM_K_ROW, amk::k_row32<L2><<<rows, C32::THREADS, C32::SMEM, h->stream>>>(A, spec, l1, rows, h->d_tw.p));
+            TRY(set_smem(amk::k_row32<L2, MODE>, C32::SMEM));
+            LAUNCH(h, AM_K_ROW, amk::k_row32<L2, MODE><<<rows, C32::THREADS, C32::SMEM, h->stream>>>(A, spec, B, l1, rows, h->d_tw.p));
             return AM_OK;
         }
     }
@@ -776,8 +776,8 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     const long long seg_c_len = ((K * C + std::max<long long>(ov - m + 1, 0) + 1 + 3) / 4) * 4;   // keeps float4 alignment per snippet
     TRY(h->d_c.reserve((size_t)seg_c_len * S));
     const long long tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
-    TRY(h->d_tmin.reserve((size_t)(K * tiles_stride)));
-    TRY(h->d_tmax.reserve((size_t)(K * tiles_stride)));
+    TRY(h->d_tmin.reserve((size_t)(K * tiles_stride) * S));
+    TRY(h->d_tmax.reserve((size_t)(K * tiles_stride) * S));
     const int pk_cap = h->cfg.max_peaks_per_chunk ? (int)h->cfg.max_peaks_per_chunk : 1024;
     size_t pk_smem = (size_t)pk_cap * (2 * sizeof(unsigned) + 4 * sizeof(float) + 1);
     if (pk_smem > 200 * 1024) return fail(AM_ERR_INVALID, "max_peaks_per_chunk %d too large", pk_cap);
@@ -823,13 +823,11 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
         amp::ChunkGeom cg;
         cg.C = C; cg.ov = ov; cg.m = m; cg.total = L; cg.first_chunk = i0; cg.c_g0 = g0; cg.tiles_stride = (int)tiles_stride;
         dim3 tgrid((unsigned)((tiles_stride + 7) / 8), (unsigned)(i1 - i0));
-        for (size_t sn = 0; sn < S; ++sn) {
-            const float *cs = h->d_c.p + sn * (size_t)seg_c_len;
-            LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid, 256, 0, h->stream>>>(cs, cg, h->d_tmin.p, h->d_tmax.p));
-            LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<<<(unsigned)(i1 - i0), 256, pk_smem, h->stream>>>(
-                                            cs, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist, pk_cap, sm_tiles,
-                                            (unsigned)sn, po));
-        }
+        cg.c_stride = seg_c_len;
+        dim3 tgrid3(tgrid.x, tgrid.y, (unsigned)S), pgrid((unsigned)(i1 - i0), (unsigned)S);
+        LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid3, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p));
+        LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<<<pgrid, 256, pk_smem, h->stream>>>(
+                                        h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist, pk_cap, sm_tiles, po));
     }
     unsigned long long cnt[2] = {0, 0};
     CU(cudaMemcpyAsync(cnt, h->d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));

@@ -411,13 +411,17 @@ k_row(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restric
 // transform instead of three.  k_row is bound by the shared-memory pipe (768 KB of exchange traffic per
 // row at 128 B/clk) and FP issue, so a third less exchange traffic and one twiddled stage less is what
 // this variant buys; it pays with 128 registers per thread (256 threads per row, 2 CTAs per SM).
+#ifndef AM_ROW32_MINB
+#define AM_ROW32_MINB 2
+#endif
 template <int L2> struct Row32Cfg {
     static constexpr int THREADS = (1 << L2) / 32;
     static constexpr size_t SMEM = (size_t)RegFFT<L2, 0, false, 32>::SMEM_ELEMS * sizeof(float2);
 };
-template <int L2>
-__global__ void __launch_bounds__(Row32Cfg<L2>::THREADS, 2)
-k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, int log2n1, int rows, const float2 *__restrict__ tw) {
+template <int L2, int MODE>
+__global__ void __launch_bounds__(Row32Cfg<L2>::THREADS, AM_ROW32_MINB)
+k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restrict__ Bout, int log2n1, int rows,
+        const float2 *__restrict__ tw) {
     typedef RegFFT<L2, 0, false, 32> F;
     typedef RegFFT<L2, 0, true, 32> I;
     extern __shared__ float2 sm[];
@@ -425,27 +429,40 @@ k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, int log2n1, int
     const int row = blockIdx.x;
     float2 *Ar = A + ((size_t)row << L2);
     float2 v[32];
+    if constexpr (MODE != ROW_INVERSE) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        int idx, t;
-        F::template in_coord<0>(gtid, j, idx, t);
-        v[j] = Ar[idx];
+        for (int j = 0; j < 32; ++j) {
+            int idx, t;
+            F::template in_coord<0>(gtid, j, idx, t);
+            v[j] = Ar[idx];
+        }
+        F::run(v, sm, gtid, tw);
+        if constexpr (MODE == ROW_FORWARD) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                int idx, t;
+                F::out_coord(gtid, j, idx, t);
+                Ar[idx] = v[j];
+            }
+            return;
+        }
     }
-    F::run(v, sm, gtid, tw);
     const float2 *Sr = spec + ((size_t)(row & ((1 << log2n1) - 1)) << L2);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         int idx, t;
-        I::template in_coord<0>(gtid, j, idx, t);
+        I::template in_coord<0>(gtid, j, idx, t);            // == F::out_coord: no exchange across the multiply
+        if constexpr (MODE == ROW_INVERSE) v[j] = Ar[idx];
         v[j] = amfft::cmul(v[j], __ldg(&Sr[idx]));
     }
-    __syncthreads();
+    if constexpr (MODE == ROW_FUSED) __syncthreads();
     I::run(v, sm, gtid, tw);
+    float2 *Or = (MODE == ROW_INVERSE) ? Bout + ((size_t)row << L2) : Ar;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         int idx, t;
         I::out_coord(gtid, j, idx, t);
-        Ar[idx] = v[j];
+        Or[idx] = v[j];
     }
 }
 

@@ -29,6 +29,7 @@ struct DevPeak {                        // mirrors am_peak (include/audio_matche
 };
 
 struct ChunkGeom {
+    long long c_stride;                 // floats between the correlation buffers of consecutive snippets (grid z)
     long long C, ov, m;                 // samples
     long long total;                    // virtual stream length (with lead/tail padding)
     long long first_chunk;              // global index of the segment's first chunk
@@ -53,7 +54,7 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// grid (ceil(tiles_stride / 8), chunks in segment), 256 threads: one 1024-sample tile per warp,
+// grid (ceil(tiles_stride / 8), chunks in segment, snippets), 256 threads: one 1024-sample tile per warp,
 // eight independent float4 loads in flight per lane
 __global__ void __launch_bounds__(256)
 k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin, float *__restrict__ tmax) {
@@ -63,7 +64,7 @@ k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin
     const long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const long long k0 = tile << TP_LOG2;
     if (k0 >= V) return;
-    const float *y = c + (g.C * chunk - g.c_g0) + k0;
+    const float *y = c + blockIdx.z * g.c_stride + (g.C * chunk - g.c_g0) + k0;
     const long long left = V - k0;
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
     if (left >= TP && (((size_t)y) & 15) == 0) {
@@ -85,7 +86,7 @@ k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin
     mn = warp_min(mn);
     mx = warp_max(mx);
     if (lane == 0) {
-        size_t o = (size_t)blockIdx.y * g.tiles_stride + tile;
+        size_t o = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * g.tiles_stride + tile;
         tmin[o] = mn;
         tmax[o] = mx;
     }
@@ -176,11 +177,11 @@ struct PeakOut {
 };
 
 // dynamic shared memory: [2 * sm_tiles floats: the chunk's tile summaries, when they fit] +
-// pk_cap * (2*u32 + 4*f32 + u8).   grid = chunks in segment, 256 threads
+// pk_cap * (2*u32 + 4*f32 + u8).   grid = (chunks in segment, snippets), 256 threads
 __global__ void __launch_bounds__(256)
 k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict__ tmin_all,
               const float *__restrict__ tmax_all, float min_prom, unsigned long long min_dist, int pk_cap,
-              int sm_tiles, unsigned snippet_id, PeakOut out) {
+              int sm_tiles, PeakOut out) {
     extern __shared__ unsigned char smraw[];
     float *s_tmin = (float *)smraw, *s_tmax = s_tmin + sm_tiles;
     unsigned *p_start = (unsigned *)(s_tmax + sm_tiles);
@@ -199,9 +200,10 @@ k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict_
     const long long chunk = g.first_chunk + blockIdx.x;
     const long long V = chunk_valid_len(g, chunk);
     if (V < 3) return;                                              // endpoints are never peaks
-    const float *y = c + (g.C * chunk - g.c_g0);
-    const float *tmin = tmin_all + (size_t)blockIdx.x * g.tiles_stride;
-    const float *tmax = tmax_all + (size_t)blockIdx.x * g.tiles_stride;
+    const unsigned snippet_id = blockIdx.y;
+    const float *y = c + snippet_id * g.c_stride + (g.C * chunk - g.c_g0);
+    const float *tmin = tmin_all + ((size_t)snippet_id * gridDim.x + blockIdx.x) * g.tiles_stride;
+    const float *tmax = tmax_all + ((size_t)snippet_id * gridDim.x + blockIdx.x) * g.tiles_stride;
     const long long ntiles = (V + TP - 1) >> TP_LOG2;
     if (ntiles <= sm_tiles) {                                       // stage the summaries: the walks re-read them
         for (int t = tid; t < ntiles; t += 256) { s_tmin[t] = tmin[t]; s_tmax[t] = tmax[t]; }

@@ -357,7 +357,8 @@ am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0
     }
     float2 *spec_all;
     TRY(get_spectrum(h, log2n, &spec_all));
-    const long long N = 1ll << log2n, VN = N - (long long)h->m + 1;
+    long long N = 1ll << log2n, VN = N - (long long)h->m + 1;
+    if (VN >= 4096) VN &= ~31ll;        // blocks advance by a multiple of 32 frames: 16-byte aligned PCM rows, 128-byte aligned output rows
     const unsigned long long nblocks = (unsigned long long)((g1 - g0 + VN - 1) / VN);
     const unsigned long long pairs_total = (nblocks + 1) / 2;
     int l1, l2;

@@ -210,6 +210,45 @@ __device__ __forceinline__ void load_tile_fast(float2 (&v)[F::EPT], const BlockG
     }
 }
 
+
+// Mono int16 tile through shared memory with 128-bit global loads: the tile's rows are 16 samples
+// (32 bytes) of each block; every (row, half-row) unit is fetched with one LDG.128 per block, the two
+// blocks are interleaved as (re, im) int16 pairs in one 32-bit word per element, and the threads then
+// pick their stage-0 inputs with conflict-free LDS.32.  Needs 16-byte aligned rows (block advance V_N
+// and segment starts multiples of 8 frames), which the host arranges; anything else takes the scalar path.
+template <class F, int LT, int L1, int THREADS>
+__device__ __forceinline__ void load_tile_i16_staged(float2 (&v)[F::EPT], const BlockGroup &g, long long f0, int log2n2,
+                                                      int tid, unsigned *sraw) {
+    static_assert(LT == 4, "16-column tiles");
+    const short *x = (const short *)g.sv.x + f0;                // f0 already includes the tile's column offset
+#pragma unroll
+    for (int u = tid; u < (2 << L1); u += THREADS) {
+        const int n1 = u >> 1, half = u & 1;
+        const short *p = x + ((long long)n1 << log2n2) + half * 8;
+        const uint4 re = __ldg((const uint4 *)p);
+        const uint4 im = __ldg((const uint4 *)(p + g.VN));
+        uint4 a, b;
+        a.x = __byte_perm(re.x, im.x, 0x5410); a.y = __byte_perm(re.x, im.x, 0x7632);
+        a.z = __byte_perm(re.y, im.y, 0x5410); a.w = __byte_perm(re.y, im.y, 0x7632);
+        b.x = __byte_perm(re.z, im.z, 0x5410); b.y = __byte_perm(re.z, im.z, 0x7632);
+        b.z = __byte_perm(re.w, im.w, 0x5410); b.w = __byte_perm(re.w, im.w, 0x7632);
+        uint4 *dst = (uint4 *)(sraw + n1 * 16 + half * 8);
+        dst[0] = a;
+        dst[1] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < F::EPT; ++j) {
+        int idx, t;
+        F::template in_coord<0>(tid, j, idx, t);
+        const unsigned w = sraw[idx * 16 + t];
+        const float re = __fmul_rn(s16_to_f32((int)(short)(w & 0xffffu)), 1.0f / 65535.0f);
+        const float im = __fmul_rn(s16_to_f32((int)w >> 16), 1.0f / 65535.0f);
+        v[j] = make_float2(re, im);
+    }
+    __syncthreads();                                            // the buffer becomes the exchange buffer
+}
+
 // grid (N2 / T, pairs).  A[pair][k1][n2] = W_N^{n2 k1} * sum_{n1} z[n1 N2 + n2] W_N1^{n1 k1}
 template <int L1, int LT, int E>
 __global__ void __launch_bounds__(ColCfg<L1, LT, E>::THREADS, ColCfg<L1, LT, E>::MINB)
@@ -238,8 +277,16 @@ k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__rest
         }
     }
     if (pair_in_range(g.sv, v0, g.VN, 1ll << (L1 + log2n2), 2 * pair + 1 < g.nblocks)) {
-        if (g.sv.fmt == FMT_I16_MONO) load_tile_fast<FMT_I16_MONO, F, Cfg::LT>(v, g, v0, log2n2, n2_0, tid);
-        else if (g.sv.fmt == FMT_I16_STEREO) load_tile_fast<FMT_I16_STEREO, F, Cfg::LT>(v, g, v0, log2n2, n2_0, tid);
+        if (g.sv.fmt == FMT_I16_MONO) {
+            const long long f0 = v0 - g.sv.lead - g.sv.buf_first + n2_0;
+            bool staged = false;
+            if constexpr (Cfg::LT == 4 && L1 >= 5)
+                if (((f0 | g.VN) & 7) == 0 && (((size_t)g.sv.x) & 15) == 0) {
+                    load_tile_i16_staged<F, Cfg::LT, L1, Cfg::THREADS>(v, g, f0, log2n2, tid, (unsigned *)sm_all);
+                    staged = true;
+                }
+            if (!staged) load_tile_fast<FMT_I16_MONO, F, Cfg::LT>(v, g, v0, log2n2, n2_0, tid);
+        } else if (g.sv.fmt == FMT_I16_STEREO) load_tile_fast<FMT_I16_STEREO, F, Cfg::LT>(v, g, v0, log2n2, n2_0, tid);
         else load_tile_fast<FMT_F32_MONO, F, Cfg::LT>(v, g, v0, log2n2, n2_0, tid);
     } else {
 #pragma unroll

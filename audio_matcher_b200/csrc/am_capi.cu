@@ -399,18 +399,6 @@ am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0
 
 am_status init_common(am_matcher *h, uint32_t sr, const am_config *cfg) {
     CU(cudaGetDevice(&h->device));
-    {   // experiment knobs (both default off): L2 prefetch distance in CTAs, first-wave stagger in ns
-        const char *v = getenv("AM_PREFETCH_CTAS");
-        if (v && *v) {
-            int pf = atoi(v);
-            CU(cudaMemcpyToSymbol(amk::c_prefetch_ctas, &pf, sizeof pf));
-        }
-        v = getenv("AM_STAGGER_NS");
-        if (v && *v) {
-            int st = atoi(v);
-            CU(cudaMemcpyToSymbol(amk::c_stagger_ns, &st, sizeof st));
-        }
-    }
     h->sr = sr;
     if (cfg) h->cfg = *cfg; else am_config_default(&h->cfg);
     if (h->cfg.overlap_s < 0) h->cfg.overlap_s = (double)h->m / (double)sr;

@@ -70,18 +70,6 @@ __device__ __forceinline__ bool pair_in_range(const StreamView &s, long long v0,
     return two && lo >= s.buf_first && hi <= lim;
 }
 
-// fire-and-forget L2 prefetch of the 128-byte line holding p (no register, no scoreboard)
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// How many CTAs ahead the kernels prefetch: the block scheduler hands out CTAs in index order, so the
-// tile `pf` CTAs ahead is the one that will be loaded next by whichever SM retires a CTA.
-__constant__ int c_prefetch_ctas = 0;
-// Experiment knob: first-wave CTAs start after a pseudo-random delay (units of this many ns, 0..15)
-// so that the SMs' load / transform / store phases do not stay in lock-step across the GPU.
-__constant__ int c_stagger_ns = 0;
-__device__ __forceinline__ void stagger_first_wave(unsigned linear_cta) {
-    if (c_stagger_ns > 0 && linear_cta < 296u) __nanosleep(((linear_cta * 2654435761u) >> 28) * (unsigned)c_stagger_ns);
-}
-
 // One launch group of overlap-save blocks.
 struct BlockGroup {
     StreamView sv;
@@ -261,21 +249,6 @@ k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__rest
     const int n2_0 = blockIdx.x << Cfg::LT;
     float2 v[EPT];
     const long long v0 = g.g0 + (long long)(2 * pair) * g.VN;
-    stagger_first_wave(blockIdx.y * gridDim.x + blockIdx.x);
-    if (c_prefetch_ctas > 0) {   // warm L2 for the PCM rows of the tile a later CTA will load
-        const long long lin = (long long)pair * gridDim.x + blockIdx.x + c_prefetch_ctas;
-        const long long pp = lin / gridDim.x, pb = lin % gridDim.x;
-        const long long pv0 = g.g0 + 2 * pp * g.VN;
-        if (pp < gridDim.y && pair_in_range(g.sv, pv0, g.VN, 1ll << (L1 + log2n2), 2 * pp + 1 < g.nblocks)) {
-            const size_t fb = g.sv.fmt == FMT_I16_MONO ? 2 : 4;
-            const long long f0 = pv0 - g.sv.lead - g.sv.buf_first + (pb << Cfg::LT);
-            for (int n1 = tid; n1 < (1 << L1); n1 += Cfg::THREADS) {
-                const char *p = (const char *)g.sv.x + (size_t)(f0 + ((long long)n1 << log2n2)) * fb;
-                prefetch_l2(p);
-                prefetch_l2(p + (size_t)g.VN * fb);
-            }
-        }
-    }
     if (pair_in_range(g.sv, v0, g.VN, 1ll << (L1 + log2n2), 2 * pair + 1 < g.nblocks)) {
         if (g.sv.fmt == FMT_I16_MONO) {
             const long long f0 = v0 - g.sv.lead - g.sv.buf_first + n2_0;
@@ -325,14 +298,6 @@ k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *
     const int n2_0 = blockIdx.x << Cfg::LT;
     const float two_over_n = 2.0f / (float)(1u << (L1 + log2n2));
     const float2 *Ap = A + ((size_t)pair << (L1 + log2n2));
-    stagger_first_wave(blockIdx.y * gridDim.x + blockIdx.x);
-    if (c_prefetch_ctas > 0) {   // warm L2 for the tile a later CTA will load (one 128-byte row segment per thread)
-        const long long lin = (long long)pair * gridDim.x + blockIdx.x + c_prefetch_ctas;
-        const long long pp = lin / gridDim.x, pb = lin % gridDim.x;
-        if (pp < gridDim.y)
-            for (int k1 = tid; k1 < (1 << L1); k1 += Cfg::THREADS)
-                prefetch_l2(A + ((size_t)pp << (L1 + log2n2)) + ((size_t)k1 << log2n2) + (pb << Cfg::LT));
-    }
     float2 v[EPT];
     constexpr int RB = I::bits_at(0), R = 1 << RB, NB = EPT / R;
 #pragma unroll
@@ -399,16 +364,6 @@ k_row(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restric
     const bool active = row < rows;
     if (!active) row = rows - 1;
     float2 *Ar = A + ((size_t)row << L2);
-    stagger_first_wave(blockIdx.x);
-    {   // warm L2 for the row (and its spectrum row) a later CTA will load: one 128-byte line per thread
-        const int prow = row + c_prefetch_ctas * Cfg::G;
-        if (c_prefetch_ctas > 0 && prow < rows) {
-            for (int i = gtid * 16; i < (1 << L2); i += Cfg::GT * 16) {
-                prefetch_l2(A + ((size_t)prow << L2) + i);
-                if (MODE != ROW_FORWARD) prefetch_l2(spec + ((size_t)(prow & ((1 << log2n1) - 1)) << L2) + i);
-            }
-        }
-    }
     float2 v[EPT];
     if constexpr (MODE != ROW_INVERSE) {
 #pragma unroll

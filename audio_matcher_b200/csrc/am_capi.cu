@@ -197,7 +197,11 @@ template <int L1, int LT, int E, bool INV> am_status launch_col_t(am_matcher *h,
 }
 template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::BlockGroup &g, int l2, float2 *A) {
     static const int lt_env = [] { const char *v = getenv("AM_COL_LT"); return v && *v ? atoi(v) : 0; }();
-    static const int ept = [] { const char *v = getenv("AM_COL_EPT"); return v && *v ? atoi(v) : 32; }();
+    // elements per thread: 16 for the forward tiles (more warps hide the PCM staging), 32 for the inverse
+    // tiles (one exchange, 80 registers, 3 CTAs per SM) -- measured; AM_COL_EPT_FWD / AM_COL_EPT_INV override
+    static const int ept_fwd = [] { const char *v = getenv("AM_COL_EPT_FWD"); return v && *v ? atoi(v) : 16; }();
+    static const int ept_inv = [] { const char *v = getenv("AM_COL_EPT_INV"); return v && *v ? atoi(v) : 32; }();
+    const int ept = INV ? ept_inv : ept_fwd;
     switch (l1) {
 #define C_(L) case L: return launch_col_t<L, amk::col_default_lt(L), 16, INV>(h, g, l2, A);
         C_(4) C_(5) C_(6) C_(7) C_(11)

@@ -149,6 +149,9 @@ k_small(BlockGroup g, const float2 *__restrict__ spec, const float2 *__restrict_
 }
 
 // ---- four-step path ---------------------------------------------------------------
+#ifndef AM_COLFWD_3
+#define AM_COLFWD_3 0
+#endif
 // default tile width (log2 columns): N1*T >= 2048 elements and <= 64 KB of exchange buffer
 constexpr int col_default_lt(int l1) { return l1 >= 10 ? 13 - l1 : (l1 >= 7 ? 4 : 11 - l1); }
 template <int L1, int LT_ = col_default_lt(L1), int E_ = 16> struct ColCfg {
@@ -159,6 +162,7 @@ template <int L1, int LT_ = col_default_lt(L1), int E_ = 16> struct ColCfg {
     static constexpr int MINB = THREADS >= 1024 ? 1 : (1024 * 16 / E) / THREADS;   // <= 64 (E = 16) / 128 (E = 32) registers
     // the inverse kernel fits 80 registers without spilling: a third resident CTA hides more load latency
     static constexpr int MINB_INV = (E == 32 && THREADS == 256) ? 3 : MINB;
+    static constexpr int MINB_FWD = AM_COLFWD_3 ? MINB_INV : MINB;
     static constexpr size_t SMEM = (size_t)RegFFT<L1, LT, false, E>::SMEM_ELEMS * sizeof(float2);
 };
 
@@ -239,7 +243,7 @@ __device__ __forceinline__ void load_tile_i16_staged(float2 (&v)[F::EPT], const 
 
 // grid (N2 / T, pairs).  A[pair][k1][n2] = W_N^{n2 k1} * sum_{n1} z[n1 N2 + n2] W_N1^{n1 k1}
 template <int L1, int LT, int E>
-__global__ void __launch_bounds__(ColCfg<L1, LT, E>::THREADS, ColCfg<L1, LT, E>::MINB)
+__global__ void __launch_bounds__(ColCfg<L1, LT, E>::THREADS, ColCfg<L1, LT, E>::MINB_FWD)
 k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__restrict__ tw) {
     typedef ColCfg<L1, LT, E> Cfg;
     typedef RegFFT<L1, Cfg::LT, false, E> F;

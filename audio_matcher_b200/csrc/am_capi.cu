@@ -213,8 +213,8 @@ template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::Block
         if (ept == 32) return launch_col_t<9, 4, 32, INV>(h, g, l2, A);
         if (lt_env == 3) return launch_col_t<9, 3, 16, INV>(h, g, l2, A);
         return launch_col_t<9, 4, 16, INV>(h, g, l2, A);
-    case 10:
-        if (ept == 32) return launch_col_t<10, 4, 32, INV>(h, g, l2, A);
+    case 10:                                  // 1024-point columns: 16 elements per thread measured faster both ways
+        if (ept == 32 && getenv("AM_COL10_EPT32")) return launch_col_t<10, 4, 32, INV>(h, g, l2, A);
         if (lt_env == 4) return launch_col_t<10, 4, 16, INV>(h, g, l2, A);
         return launch_col_t<10, 3, 16, INV>(h, g, l2, A);
     }

@@ -149,9 +149,6 @@ k_small(BlockGroup g, const float2 *__restrict__ spec, const float2 *__restrict_
 }
 
 // ---- four-step path ---------------------------------------------------------------
-#ifndef AM_COLFWD_3
-#define AM_COLFWD_3 0
-#endif
 // default tile width (log2 columns): N1*T >= 2048 elements and <= 64 KB of exchange buffer
 constexpr int col_default_lt(int l1) { return l1 >= 10 ? 13 - l1 : (l1 >= 7 ? 4 : 11 - l1); }
 template <int L1, int LT_ = col_default_lt(L1), int E_ = 16> struct ColCfg {
@@ -162,7 +159,7 @@ template <int L1, int LT_ = col_default_lt(L1), int E_ = 16> struct ColCfg {
     static constexpr int MINB = THREADS >= 1024 ? 1 : (1024 * 16 / E) / THREADS;   // <= 64 (E = 16) / 128 (E = 32) registers
     // the inverse kernel fits 80 registers without spilling: a third resident CTA hides more load latency
     static constexpr int MINB_INV = (E == 32 && THREADS == 256) ? 3 : MINB;
-    static constexpr int MINB_FWD = AM_COLFWD_3 ? MINB_INV : MINB;
+    static constexpr int MINB_FWD = MINB;        // the forward kernel spills at 80 registers (measured slower)
     static constexpr size_t SMEM = (size_t)RegFFT<L1, LT, false, E>::SMEM_ELEMS * sizeof(float2);
 };
 
@@ -417,15 +414,12 @@ k_row(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restric
 // transform instead of three.  k_row is bound by the shared-memory pipe (768 KB of exchange traffic per
 // row at 128 B/clk) and FP issue, so a third less exchange traffic and one twiddled stage less is what
 // this variant buys; it pays with 128 registers per thread (256 threads per row, 2 CTAs per SM).
-#ifndef AM_ROW32_MINB
-#define AM_ROW32_MINB 2
-#endif
 template <int L2> struct Row32Cfg {
     static constexpr int THREADS = (1 << L2) / 32;
     static constexpr size_t SMEM = (size_t)RegFFT<L2, 0, false, 32>::SMEM_ELEMS * sizeof(float2);
 };
 template <int L2, int MODE>
-__global__ void __launch_bounds__(Row32Cfg<L2>::THREADS, AM_ROW32_MINB)
+__global__ void __launch_bounds__(Row32Cfg<L2>::THREADS, 2)
 k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restrict__ Bout, int log2n1, int rows,
         const float2 *__restrict__ tw) {
     typedef RegFFT<L2, 0, false, 32> F;

@@ -154,6 +154,34 @@ def test_calc_chunks_random_vs_oracle(am, orc, seed, dist, prom, maxpk):
     _assert_peaks(got, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
 
 
+def test_unaligned_device_buffer_and_dc_offset(am, orc):
+    """The 128-bit staged PCM loads need 16-byte aligned rows; a device view that starts at an odd sample must take
+    the scalar load path and give the same peaks.  A strong DC offset in the stream must not hurt the scores."""
+    import torch
+    sr, m = 8000, 4000
+    pcm = orc.synth_pcm16(31, 0, sr * 37 + 1)
+    snip = orc.synth_pcm16(32, 0, m)
+    for k, o in enumerate([7001, 90000, 170003, 250000]):
+        orc.synth_plant(pcm, 1, snip, o, k % 3)
+    conf = am.Config(chunk_size=5.0, peak_config=am.PeakConfig(2.0, 0.13), fft_log2=15)
+    algo = am.CudaConvolve(snip, sr=sr, config=conf)
+    dev = torch.from_numpy(pcm).cuda()
+    for view, host in ((dev[1:], pcm[1:]), (dev[:-1], pcm[:-1])):            # odd start / aligned start
+        got = am.calc_chunks(sr, view, algo, True, conf)
+        x, s = orc.pcm16_to_f32(np.ascontiguousarray(host)), orc.pcm16_to_f32(snip)
+        ref = orc.calc_chunks(x, s, sr, orc.make_config(5.0, m / sr, 2.0, 0.13), scale=True, precision=64)
+        assert len(ref) >= 3
+        _assert_peaks(got, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+    shifted = (pcm.astype(np.int32) // 2 + 12000).astype(np.int16)             # large DC component
+    got = am.calc_chunks(sr, shifted, algo, True, conf)
+    x = orc.pcm16_to_f32(shifted)
+    ref = orc.calc_chunks(x, orc.pcm16_to_f32(snip), sr, orc.make_config(5.0, m / sr, 2.0, 0.13), scale=True, precision=64)
+    assert [p.position.start for p in got] == [p.start for p in ref] and len(ref) >= 1
+    for a, b in zip(got, ref):
+        assert abs(a.height - b.height) <= REL_TOL * abs(b.height)
+    algo.close()
+
+
 def test_batch_equals_independent_runs(am, orc):
     """BASELINE config 3 semantics: a batch of snippets == one reference-semantics run per snippet."""
     sr, m = 8000, 3000

@@ -41,7 +41,8 @@ class AmPeak(C.Structure):
 class AmStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("fft_blocks", C.c_uint64), ("frames", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("fft_log2", C.c_uint32),
-                ("log2_n1", C.c_uint32), ("log2_n2", C.c_uint32), ("chunks", C.c_uint32)]
+                ("log2_n1", C.c_uint32), ("log2_n2", C.c_uint32), ("chunks", C.c_uint32),
+                ("summary_mode", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class AmKernelTime(C.Structure):

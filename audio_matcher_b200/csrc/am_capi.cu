@@ -103,6 +103,7 @@ struct am_matcher {
     std::map<int, float2 *> spectra;         // log2n -> [S][N] conjugate spectra
     DevBuf<float2> d_A, d_B;
     DevBuf<float> d_c, d_tmin, d_tmax;
+    DevBuf<float4> d_rsum;                   // summary mode: one record per aligned run of 16 outputs
     DevBuf<amp::DevPeak> d_peaks;
     DevBuf<unsigned long long> d_count;   // [0] = count, [1] low 32 bits = flags
     DevBuf<unsigned char> d_stage[2];
@@ -187,8 +188,8 @@ template <int L1, int LT, int E, bool INV> am_status launch_col_t(am_matcher *h,
     int pairs = (g.nblocks + 1) / 2;
     dim3 grid((1u << l2) >> Cfg::LT, pairs);
     if (INV) {
-        TRY(set_smem(amk::k_col_inv<L1, LT, E>, Cfg::SMEM));
-        LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT, E><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
+        TRY(set_smem(amk::k_col_inv<L1, LT, E>, Cfg::SMEM_INV));
+        LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT, E><<<grid, Cfg::THREADS, Cfg::SMEM_INV, h->stream>>>(g, l2, A, h->d_tw.p));
     } else {
         TRY(set_smem(amk::k_col_fwd<L1, LT, E>, Cfg::SMEM));
         LAUNCH(h, AM_K_COL_FWD, amk::k_col_fwd<L1, LT, E><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
@@ -219,6 +220,18 @@ template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::Block
         return launch_col_t<10, 3, 16, INV>(h, g, l2, A);
     }
     return fail(AM_ERR_UNSUPPORTED, "column length 2^%d not built", l1);
+}
+
+// does launch_col<true> pick a 16-column-tile kernel (the ones with the run-summary epilogue) for this column length?
+bool col_inv_writes_runs(int l1) {
+    const char *v = getenv("AM_COL_LT");
+    const int lt_env = v && *v ? atoi(v) : 0;
+    v = getenv("AM_COL_EPT_INV");
+    const int ept_inv = v && *v ? atoi(v) : 32;
+    if (l1 == 7) return true;
+    if (l1 == 8) return lt_env != 5;
+    if (l1 == 9) return ept_inv == 32 || lt_env != 3;
+    return false;
 }
 
 template <int L2, int MODE>
@@ -344,7 +357,8 @@ am_status get_spectrum(am_matcher *h, int log2n, float2 **out) {
 // With several snippets the stream-side work (column pass + forward row pass) is done once per block
 // group and only the multiply + inverse passes run per snippet.
 am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0, long long g1, int log2n, int scale,
-                          float *c, size_t c_stride, long long c_g0, size_t s0, size_t ns) {
+                          float *c, size_t c_stride, long long c_g0, size_t s0, size_t ns, float4 *rsum = nullptr,
+                          float theta = 0.f) {
     if (g1 <= g0 || ns == 0) return AM_OK;
     const float inv_n = (float)(1.0 / (double)(1ull << log2n));
     auto scalar_of = [&](size_t sn) { return inv_n * (scale ? h->inv_ac[sn] : 1.0f); };
@@ -370,7 +384,7 @@ am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0
     h->stats.fft_log2 = log2n; h->stats.log2_n1 = l1; h->stats.log2_n2 = l2;
     h->stats.fft_blocks += nblocks;
     amk::BlockGroup g;
-    g.sv = sv; g.g_end = g1; g.VN = VN; g.c = c; g.c_g0 = c_g0; g.scalar = 0.f;
+    g.sv = sv; g.g_end = g1; g.VN = VN; g.c = c; g.c_g0 = c_g0; g.scalar = 0.f; g.rsum = rsum; g.theta = theta;
     unsigned long long ppg = 1u << 20;     // pairs per launch
     if (l1 != 0) TRY(ensure_workspace(h, log2n, pairs_total, ppg));
     for (unsigned long long p0 = 0; p0 < pairs_total; p0 += ppg) {
@@ -393,6 +407,7 @@ am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0
             TRY(launch_row<amk::ROW_FORWARD>(h, l2, h->d_A.p, nullptr, nullptr, l1, rows));
             for (size_t j = 0; j < ns; ++j) {
                 g.c = c + j * c_stride; g.scalar = scalar_of(s0 + j);
+                if (rsum) g.rsum = rsum + j * (c_stride >> 4);
                 TRY(launch_row<amk::ROW_INVERSE>(h, l2, h->d_A.p, spec_all + (s0 + j) * (size_t)N, h->d_B.p, l1, rows));
                 TRY(launch_col<true>(h, l1, g, l2, h->d_B.p));
             }
@@ -574,7 +589,7 @@ void am_matcher_destroy(am_matcher *h) {
     cudaDeviceSynchronize();
     for (auto &kv : h->spectra) cudaFree(kv.second);
     h->d_snip.release(); h->d_tw.release(); h->d_A.release(); h->d_B.release(); h->d_c.release(); h->d_tmin.release();
-    h->d_tmax.release(); h->d_peaks.release(); h->d_count.release();
+    h->d_tmax.release(); h->d_rsum.release(); h->d_peaks.release(); h->d_count.release();
     h->d_stage[0].release(); h->d_stage[1].release();
     for (int i = 0; i < 2; ++i) {
         if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
@@ -759,15 +774,30 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     int log2n;
     TRY(choose_log2n(h, outputs, log2n));
 
-    // segments of K logical chunks share one dense correlation buffer per snippet; a batch keeps at
+    // Summary mode: the inverse column kernel writes one {min, max, first, last} record per aligned run of 16
+    // outputs and the outputs themselves only where the run maximum reaches theta = prominence / 2; the peak
+    // kernels work from the records.  Needs 16-column tiles, run-aligned chunks and a positive threshold; if a
+    // chunk turns out to violate the bound (min_prom + chunk_min < theta) or has an unsupported partial run the
+    // kernels raise FLAG_NEED_DENSE and the pass is repeated with the dense correlation.
+    int sp_l1, sp_l2;
+    split(log2n, sp_l1, sp_l2);
+    bool summary = col_inv_writes_runs(sp_l1) && h->m > (size_t)amk::DIRECT_MAX_M && (C % 16) == 0 &&
+                   h->cfg.prominence > 0.f && std::isfinite(h->cfg.prominence);
+    {
+        static const int env = [] { const char *v = getenv("AM_SUMMARY"); return v && *v ? atoi(v) : 1; }();
+        if (!env) summary = false;
+    }
+
+    // segments of K logical chunks share one correlation buffer per snippet; a batch keeps at
     // least ~48 M outputs per snippet per segment so that a segment still spans several block pairs
     const size_t S = h->S;
     size_t seg_floats = (env_mb("AM_SEGMENT_MB", 1024) << 20) / sizeof(float) / S;
     if (S > 1) seg_floats = std::max<size_t>(seg_floats, (size_t)48 << 20);
     long long K = std::max<long long>(1, (long long)(seg_floats / (size_t)C));
     K = std::min<long long>(K, (long long)num_chunks);
-    const long long seg_c_len = ((K * C + std::max<long long>(ov - m + 1, 0) + 1 + 3) / 4) * 4;   // keeps float4 alignment per snippet
+    const long long seg_c_len = ((K * C + std::max<long long>(ov - m + 1, 0) + 1 + 15) / 16) * 16;   // float4 / run alignment per snippet
     TRY(h->d_c.reserve((size_t)seg_c_len * S));
+    if (summary) TRY(h->d_rsum.reserve(((size_t)seg_c_len * S) >> 4));
     const long long tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
     TRY(h->d_tmin.reserve((size_t)(K * tiles_stride) * S));
     TRY(h->d_tmax.reserve((size_t)(K * tiles_stride) * S));
@@ -777,56 +807,76 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     int sm_tiles = 0;                                        // tile summaries staged in shared memory when they fit
     if (pk_smem + (size_t)tiles_stride * 8 <= 96 * 1024) sm_tiles = (int)tiles_stride;
     pk_smem += (size_t)sm_tiles * 8;
-    TRY(set_smem(amp::k_chunk_peaks, pk_smem));
+    TRY(set_smem(amp::k_chunk_peaks<false>, pk_smem));
+    TRY(set_smem(amp::k_chunk_peaks<true>, pk_smem));
     const size_t dev_cap = std::min<size_t>((size_t)num_chunks * (size_t)pk_cap * S, (size_t)1 << 22);
     TRY(h->d_peaks.reserve(dev_cap));
-    CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
     amp::PeakOut po;
     po.peaks = h->d_peaks.p; po.cap = dev_cap; po.count = h->d_count.p; po.flags = (unsigned *)(h->d_count.p + 1);
     const unsigned long long min_dist = (unsigned long long)h->cfg.distance_s * (unsigned long long)h->sr;  // as_secs(), :228
     const size_t fb = fmt_bytes(fmt);
-
-    int seg_idx = 0;
-    for (long long i0 = c_first; i0 < c_last; i0 += K, ++seg_idx) {
-        const long long i1 = std::min(c_last, i0 + K);
-        const long long g0 = C * i0;
-        long long g1 = g0;
-        for (long long i = i1 - 1; i >= i0; --i)
-            if (chunk_end(i) > C * i) { g1 = chunk_end(i); break; }
-        if (g1 <= g0) continue;
-        amk::StreamView sv;
-        sv.fmt = (int)fmt; sv.total = L; sv.lead = 0;
-        if (mem == AM_MEM_HOST) {
-            const int b = seg_idx & 1;
-            const long long f_lo = g0, f_hi = std::min(L, g1 + m - 1);
-            const size_t bytes = (size_t)(f_hi - f_lo) * fb;
-            CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // kernels that read this buffer are done
-            TRY(h->d_stage[b].reserve(bytes));
-            CU(cudaMemcpyAsync(h->d_stage[b].p, (const unsigned char *)stream + (size_t)(f_lo - (long long)buf_first_frame) * fb,
-                               bytes, cudaMemcpyHostToDevice, h->copy_stream));
-            CU(cudaEventRecord(h->ev_up[b], h->copy_stream));
-            CU(cudaStreamWaitEvent(h->stream, h->ev_up[b], 0));
-            h->stats.h2d_bytes += bytes;
-            sv.x = h->d_stage[b].p; sv.buf_first = f_lo; sv.buf_frames = f_hi - f_lo;
-        } else {
-            sv.x = stream; sv.buf_first = (long long)buf_first_frame; sv.buf_frames = (long long)buf_frames;
-        }
-        TRY(run_correlation(h, sv, g0, g1, log2n, scale, h->d_c.p, (size_t)seg_c_len, g0, 0, S));
-        if (mem == AM_MEM_HOST) CU(cudaEventRecord(h->ev_done[seg_idx & 1], h->stream));
-        amp::ChunkGeom cg;
-        cg.C = C; cg.ov = ov; cg.m = m; cg.total = L; cg.first_chunk = i0; cg.c_g0 = g0; cg.tiles_stride = (int)tiles_stride;
-        dim3 tgrid((unsigned)((tiles_stride + 7) / 8), (unsigned)(i1 - i0));
-        cg.c_stride = seg_c_len;
-        dim3 tgrid3(tgrid.x, tgrid.y, (unsigned)S), pgrid((unsigned)(i1 - i0), (unsigned)S);
-        LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid3, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p));
-        LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<<<pgrid, 256, pk_smem, h->stream>>>(
-                                        h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist, pk_cap, sm_tiles, po));
-    }
+    const float theta = 0.5f * h->cfg.prominence;
     unsigned long long cnt[2] = {0, 0};
-    CU(cudaMemcpyAsync(cnt, h->d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+
+    // one pass over all segments: transforms + peak kernels; the counters come back in cnt
+    auto run_pass = [&](bool sum) -> am_status {
+        CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
+        int seg_idx = 0;
+        for (long long i0 = c_first; i0 < c_last; i0 += K, ++seg_idx) {
+            const long long i1 = std::min(c_last, i0 + K);
+            const long long g0 = C * i0;
+            long long g1 = g0;
+            for (long long i = i1 - 1; i >= i0; --i)
+                if (chunk_end(i) > C * i) { g1 = chunk_end(i); break; }
+            if (g1 <= g0) continue;
+            amk::StreamView sv;
+            sv.fmt = (int)fmt; sv.total = L; sv.lead = 0;
+            if (mem == AM_MEM_HOST) {
+                const int b = seg_idx & 1;
+                const long long f_lo = g0, f_hi = std::min(L, g1 + m - 1);
+                const size_t bytes = (size_t)(f_hi - f_lo) * fb;
+                CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // kernels that read this buffer are done
+                TRY(h->d_stage[b].reserve(bytes));
+                CU(cudaMemcpyAsync(h->d_stage[b].p, (const unsigned char *)stream + (size_t)(f_lo - (long long)buf_first_frame) * fb,
+                                   bytes, cudaMemcpyHostToDevice, h->copy_stream));
+                CU(cudaEventRecord(h->ev_up[b], h->copy_stream));
+                CU(cudaStreamWaitEvent(h->stream, h->ev_up[b], 0));
+                h->stats.h2d_bytes += bytes;
+                sv.x = h->d_stage[b].p; sv.buf_first = f_lo; sv.buf_frames = f_hi - f_lo;
+            } else {
+                sv.x = stream; sv.buf_first = (long long)buf_first_frame; sv.buf_frames = (long long)buf_frames;
+            }
+            TRY(run_correlation(h, sv, g0, g1, log2n, scale, h->d_c.p, (size_t)seg_c_len, g0, 0, S,
+                                sum ? h->d_rsum.p : nullptr, theta));
+            if (mem == AM_MEM_HOST) CU(cudaEventRecord(h->ev_done[seg_idx & 1], h->stream));
+            amp::ChunkGeom cg;
+            cg.C = C; cg.ov = ov; cg.m = m; cg.total = L; cg.first_chunk = i0; cg.c_g0 = g0; cg.tiles_stride = (int)tiles_stride;
+            cg.c_stride = seg_c_len; cg.seg_end = g1 - g0;
+            dim3 tgrid3((unsigned)((tiles_stride + 7) / 8), (unsigned)(i1 - i0), (unsigned)S), pgrid((unsigned)(i1 - i0), (unsigned)S);
+            if (sum) {
+                LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(h->d_rsum.p, cg, h->d_tmin.p, h->d_tmax.p, po.flags));
+                LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<true><<<pgrid, 256, pk_smem, h->stream>>>(
+                                                h->d_c.p, h->d_rsum.p, theta, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist,
+                                                pk_cap, sm_tiles, po));
+            } else {
+                LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid3, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p));
+                LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<false><<<pgrid, 256, pk_smem, h->stream>>>(
+                                                h->d_c.p, nullptr, 0.f, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist,
+                                                pk_cap, sm_tiles, po));
+            }
+        }
+        CU(cudaMemcpyAsync(cnt, h->d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->stats.d2h_bytes += sizeof cnt;
+        return AM_OK;
+    };
+    TRY(run_pass(summary));
+    h->stats.summary_mode = summary ? 1 : 0;
+    if (summary && ((unsigned)cnt[1] & amp::FLAG_NEED_DENSE)) {
+        h->stats.summary_mode = 2;                           // summary pass rejected, repeated densely
+        TRY(run_pass(false));
+    }
     prof_collect(h);
-    h->stats.d2h_bytes += sizeof cnt;
     h->stats.frames = (uint64_t)(need_hi - need_lo);
     h->stats.chunks = (uint32_t)num_chunks;
     if ((unsigned)cnt[1] & 1u)

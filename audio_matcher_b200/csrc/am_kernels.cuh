@@ -80,6 +80,11 @@ struct BlockGroup {
     float *c;           // correlation out, c[g - c_g0]
     long long c_g0;
     float scalar;       // 1/N or 1/(N sum s^2)
+    // Summary mode (k_col_inv with 16-column tiles only): for every aligned run of 16 outputs the kernel writes
+    // rsum[(g - c_g0) >> 4] = {min, max, first, last} and stores the 16 values themselves only when max >= theta.
+    // theta = -inf keeps the correlation dense.  nullptr: no records, plain dense stores.
+    float4 *rsum;
+    float theta;
 };
 
 __device__ __forceinline__ void store_pair(const BlockGroup &g, int pair, long long n, float2 val) {
@@ -161,6 +166,7 @@ template <int L1, int LT_ = col_default_lt(L1), int E_ = 16> struct ColCfg {
     static constexpr int MINB_INV = (E == 32 && THREADS == 256) ? 3 : MINB;
     static constexpr int MINB_FWD = MINB;        // the forward kernel spills at 80 registers (measured slower)
     static constexpr size_t SMEM = (size_t)RegFFT<L1, LT, false, E>::SMEM_ELEMS * sizeof(float2);
+    static constexpr size_t SMEM_INV = SMEM;     // the transposing epilogue reuses the exchange buffer (16 float2 per row, XOR swizzle)
 };
 
 // exp(-+ 2 pi i p / N), p < N <= 2^24 (p and 2/N exact in fp32)
@@ -313,6 +319,63 @@ k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *
     }
     I::run(v, sm_all, tid, tw);
     const long long o0 = g.g0 + (long long)(2 * pair) * g.VN;
+    if constexpr (Cfg::LT == 4) {
+        if (g.rsum != nullptr) {
+            // Summary epilogue: transpose the tile through the (now idle) exchange buffer so that every thread owns
+            // whole rows = aligned runs of 16 outputs of both blocks, then write one {min, max, first, last} record
+            // per run and the run itself (four 128-bit stores) only if its maximum reaches theta.
+            // rows of 16 float2 = eight 16-byte chunks; chunk c of row r lives at position c ^ (r & 7), which keeps
+            // both the column-wise float2 writes and the row-wise float4 reads free of bank conflicts
+            const int vn = (int)g.VN;
+            const bool has_im = 2 * pair + 1 < g.nblocks;
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                int n1, t;
+                I::out_coord(tid, j, n1, t);
+                sm_all[n1 * 16 + ((((t >> 1) ^ (n1 & 7)) << 1) | (t & 1))] = make_float2(v[j].x * g.scalar, v[j].y * g.scalar);
+            }
+            __syncthreads();
+            for (int row = tid; row < (1 << L1); row += Cfg::THREADS) {
+                const int nb = (row << log2n2) + n2_0;
+                if (nb >= vn) continue;                              // cropped: V_N and nb are multiples of 16
+                float re[16], im[16];
+                const float4 *src = (const float4 *)(sm_all + row * 16);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 q = src[i ^ (row & 7)];
+                    re[2 * i] = q.x; im[2 * i] = q.y; re[2 * i + 1] = q.z; im[2 * i + 1] = q.w;
+                }
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    if (blk == 1 && !has_im) break;
+                    const float *vals = blk ? im : re;
+                    const long long o = o0 + (long long)blk * vn + nb;
+                    const long long left = g.g_end - o;
+                    if (left <= 0) continue;
+                    const int valid = left < 16 ? (int)left : 16;
+                    float mn = vals[0], mx = vals[0], last = vals[0];
+#pragma unroll
+                    for (int i = 1; i < 16; ++i)
+                        if (i < valid) { mn = fminf(mn, vals[i]); mx = fmaxf(mx, vals[i]); last = vals[i]; }
+                    const long long ci = o - g.c_g0;
+                    g.rsum[ci >> 4] = make_float4(mn, mx, vals[0], last);
+                    if (mx >= g.theta) {
+                        float *dst = g.c + ci;
+                        if (valid == 16) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                ((float4 *)dst)[i] = make_float4(vals[4 * i], vals[4 * i + 1], vals[4 * i + 2], vals[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < valid) dst[i] = vals[i];
+                        }
+                    }
+                }
+            }
+            return;
+        }
+    }
     if (2 * pair + 1 < g.nblocks && o0 + 2 * g.VN <= g.g_end) {
         // both blocks entirely inside the requested output range (CTA-uniform): 32-bit crop test only
         float *c0 = g.c + (o0 - g.c_g0);

@@ -7,7 +7,8 @@
 // (window C + ov stepped by C, V = n - m + 1 outputs, audio_matcher.rs:99-104,119)
 // scopes the prominence walks, so it is reproduced here index for index.
 //
-//   k_tile_minmax   min / max of every 1024-sample tile of every chunk
+//   k_tile_minmax   min / max of every 1024-sample tile of every chunk (dense correlation)
+//   k_tile_from_runs  the same from the per-run records of k_col_inv's summary epilogue (1/4 of the bytes)
 //   k_chunk_peaks   one CTA per chunk: chunk minimum -> exact-safe candidate filter
 //                   (prominence <= height - chunk_min) -> warp-cooperative prominence
 //                   walks that skip whole tiles through the min/max summaries ->
@@ -35,6 +36,7 @@ struct ChunkGeom {
     long long first_chunk;              // global index of the segment's first chunk
     long long c_g0;                     // global offset of c[0]
     int tiles_stride;                   // tiles allocated per chunk in tmin/tmax
+    long long seg_end;                  // summary mode: index (in c) one past the segment's last output
 };
 
 __device__ __forceinline__ long long chunk_valid_len(const ChunkGeom &g, long long chunk) {
@@ -90,6 +92,169 @@ k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin
         tmin[o] = mn;
         tmax[o] = mx;
     }
+}
+
+
+// ---- summary mode -------------------------------------------------------------------------
+// k_col_inv's summary epilogue leaves, for every aligned run of 16 outputs, a record {min, max, first, last}
+// and the 16 values themselves only where max >= theta.  A chunk's outputs start run-aligned (C % 16 == 0);
+// its last run may be partial: if the chunk ends where the segment ends the record already covers only the
+// valid outputs, otherwise exactly one output may be valid (ov == m: V = C + 1) and `first` is that output.
+// Any other geometry sets FLAG_NEED_DENSE and the host repeats the call with the dense correlation.
+constexpr unsigned FLAG_OVERFLOW = 1u, FLAG_NEED_DENSE = 2u;
+
+struct RunView {
+    const float4 *rs;       // records of this chunk, rs[0] = run of the chunk's first output
+    long long nr_full;      // full runs
+    int pv;                 // valid outputs of run nr_full (0: there is no partial run)
+    bool masked;            // the partial run's record covers only the valid outputs
+    __device__ __forceinline__ long long total() const { return nr_full + (pv ? 1 : 0); }
+    __device__ __forceinline__ int count(long long r) const { return r == nr_full ? pv : 16; }
+    __device__ __forceinline__ void minmax(long long r, float &mn, float &mx) const {
+        const float4 q = __ldg(rs + r);
+        if (r == nr_full && !masked) { mn = q.z; mx = q.z; } else { mn = q.x; mx = q.y; }
+    }
+};
+__device__ __forceinline__ RunView make_run_view(const float4 *rsum, const ChunkGeom &g, long long chunk, long long V,
+                                                 unsigned snippet) {
+    RunView rv;
+    const long long cs = g.C * chunk - g.c_g0;
+    rv.rs = rsum + ((snippet * g.c_stride + cs) >> 4);
+    rv.nr_full = V >> 4;
+    rv.pv = (int)(V & 15);
+    rv.masked = (cs + V == g.seg_end);
+    return rv;
+}
+
+// grid (ceil(tiles_stride / 8), chunks in segment, snippets), 256 threads: one tile (64 runs) per warp
+__global__ void __launch_bounds__(256)
+k_tile_from_runs(const float4 *__restrict__ rsum, ChunkGeom g, float *__restrict__ tmin, float *__restrict__ tmax,
+                 unsigned *flags) {
+    const long long chunk = g.first_chunk + blockIdx.y;
+    const long long V = chunk_valid_len(g, chunk);
+    const int lane = threadIdx.x & 31;
+    const long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if ((tile << TP_LOG2) >= V) return;
+    const RunView rv = make_run_view(rsum, g, chunk, V, blockIdx.z);
+    if (rv.pv > 1 && !rv.masked && lane == 0) atomicOr(flags, FLAG_NEED_DENSE);
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const long long r = (tile << 6) + i * 32 + lane;
+        if (r < rv.total()) {
+            float a, b;
+            rv.minmax(r, a, b);
+            mn = fminf(mn, a);
+            mx = fmaxf(mx, b);
+        }
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) {
+        size_t o = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * g.tiles_stride + tile;
+        tmin[o] = mn;
+        tmax[o] = mx;
+    }
+}
+
+// walk_min for summary mode: tiles -> runs -> the one stored run that holds the first sample > h
+template <int DIR>
+__device__ float walk_min_sum(const float *__restrict__ y, const RunView &rv, long long V, const float *__restrict__ tmin,
+                              const float *__restrict__ tmax, long long from, float h) {
+    const int lane = threadIdx.x & 31;
+    float m = h;
+    bool found = false;
+    // samples [16 r + s_lo, 16 r + s_hi) of a stored run, towards DIR
+    auto raw_run = [&](long long r, int s_lo, int s_hi) {
+        const int s = (DIR < 0) ? (s_hi - 1 - lane) : (s_lo + lane);
+        const bool valid = lane < (s_hi - s_lo);
+        const float v = valid ? __ldg(y + (r << 4) + s) : CUDART_INF_F;
+        const unsigned hi = __ballot_sync(0xffffffffu, valid && v > h);
+        if (hi) {
+            const int first = __ffs(hi) - 1;
+            m = fminf(m, warp_min(lane < first ? v : CUDART_INF_F));
+            found = true;
+        } else m = fminf(m, warp_min(v));
+    };
+    // runs [ra, rb) towards DIR, 32 per step
+    auto runs = [&](long long ra, long long rb) {
+        long long done = 0;
+        const long long len = rb - ra;
+        while (done < len && !found) {
+            const long long r = (DIR < 0) ? (rb - 1 - done - lane) : (ra + done + lane);
+            const bool valid = (DIR < 0) ? (r >= ra) : (r < rb);
+            float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+            if (valid) rv.minmax(r, mn, mx);
+            const unsigned hi = __ballot_sync(0xffffffffu, valid && mx > h);
+            if (hi) {
+                const int first = __ffs(hi) - 1;
+                m = fminf(m, warp_min(lane < first ? mn : CUDART_INF_F));
+                const long long rr = (DIR < 0) ? (rb - 1 - done - first) : (ra + done + first);
+                raw_run(rr, 0, rv.count(rr));               // max > h >= theta: this run is stored
+                found = true;
+            } else {
+                m = fminf(m, warp_min(mn));
+                done += 32;
+            }
+        }
+    };
+    const long long total_runs = rv.total();
+    const long long ntiles = (V + TP - 1) >> TP_LOG2;
+    if (DIR < 0) {
+        const long long r0 = from >> 4;
+        const int s0 = (int)(from & 15);
+        if (s0) raw_run(r0, 0, s0);                         // rest of the peak's own (stored) run
+        if (!found) runs((r0 >> 6) << 6, r0);
+        long long t_hi = r0 >> 6;
+        while (!found && t_hi > 0) {
+            const long long tt = t_hi - 1 - lane;
+            const bool valid = tt >= 0;
+            const float mx = valid ? tmax[tt] : -CUDART_INF_F, mn = valid ? tmin[tt] : CUDART_INF_F;
+            const unsigned hi = __ballot_sync(0xffffffffu, valid && mx > h);
+            if (hi) {
+                const int first = __ffs(hi) - 1;
+                m = fminf(m, warp_min(lane < first ? mn : CUDART_INF_F));
+                const long long te = t_hi - 1 - first;
+                runs(te << 6, (te + 1) << 6);
+                found = true;
+            } else {
+                m = fminf(m, warp_min(mn));
+                t_hi -= 32;
+            }
+        }
+    } else {
+        long long rn = from >> 4;                           // next run to examine through its record
+        const int s0 = (int)(from & 15);
+        if (s0) {                                           // rest of the run that holds the plateau's last sample
+            const int cnt = rv.count(rn);
+            if (s0 < cnt) raw_run(rn, s0, cnt);
+            ++rn;
+        }
+        const long long t = from >> TP_LOG2;                // tile of `from`
+        long long tile_hi = (t + 1) << 6;
+        if (tile_hi > total_runs) tile_hi = total_runs;
+        if (!found && rn < tile_hi) runs(rn, tile_hi);
+        long long t_lo = t + 1;
+        while (!found && t_lo < ntiles) {
+            const long long tt = t_lo + lane;
+            const bool valid = tt < ntiles;
+            const float mx = valid ? tmax[tt] : -CUDART_INF_F, mn = valid ? tmin[tt] : CUDART_INF_F;
+            const unsigned hi = __ballot_sync(0xffffffffu, valid && mx > h);
+            if (hi) {
+                const int first = __ffs(hi) - 1;
+                m = fminf(m, warp_min(lane < first ? mn : CUDART_INF_F));
+                const long long te = t_lo + first;
+                long long e = (te + 1) << 6;
+                if (e > total_runs) e = total_runs;
+                runs(te << 6, e);
+                found = true;
+            } else {
+                m = fminf(m, warp_min(mn));
+                t_lo += 32;
+            }
+        }
+    }
+    return m;
 }
 
 // Walk from the peak towards lower (DIR = -1) or higher (DIR = +1) indices until a sample
@@ -178,10 +343,12 @@ struct PeakOut {
 
 // dynamic shared memory: [2 * sm_tiles floats: the chunk's tile summaries, when they fit] +
 // pk_cap * (2*u32 + 4*f32 + u8).   grid = (chunks in segment, snippets), 256 threads
+// SUM: summary mode -- `rsum` holds the run records, only runs with max >= theta are present in c.
+template <bool SUM>
 __global__ void __launch_bounds__(256)
-k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict__ tmin_all,
-              const float *__restrict__ tmax_all, float min_prom, unsigned long long min_dist, int pk_cap,
-              int sm_tiles, PeakOut out) {
+k_chunk_peaks(const float *__restrict__ c, const float4 *__restrict__ rsum, float theta, ChunkGeom g,
+              const float *__restrict__ tmin_all, const float *__restrict__ tmax_all, float min_prom,
+              unsigned long long min_dist, int pk_cap, int sm_tiles, PeakOut out) {
     extern __shared__ unsigned char smraw[];
     float *s_tmin = (float *)smraw, *s_tmax = s_tmin + sm_tiles;
     unsigned *p_start = (unsigned *)(s_tmax + sm_tiles);
@@ -225,6 +392,16 @@ k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict_
     }
     __syncthreads();
     const float cmin = s_cmin;
+    RunView rv;
+    if constexpr (SUM) {
+        rv = make_run_view(rsum, g, chunk, V, snippet_id);
+        // every run that can hold a candidate (max - cmin >= min_prom) or stop a walk (max > h) must be stored:
+        // guaranteed when theta <= min_prom + cmin, otherwise the host redoes the call densely
+        if (!(min_prom + cmin >= theta)) {
+            if (tid == 0) atomicOr(out.flags, FLAG_NEED_DENSE);
+            return;
+        }
+    }
 
     // (b) candidates: local maxima whose upper bound h - chunk_min on the prominence passes.
     // prominence = h - max(lmin, rmin) <= h - chunk_min (fp subtraction is monotone), so no
@@ -232,6 +409,36 @@ k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict_
     for (long long t = warp; t < ntiles; t += 8) {
         if (!(tmax[t] - cmin >= min_prom)) continue;                // warp-uniform
         long long k0 = t << TP_LOG2;
+        if constexpr (SUM) {
+            // qualifying runs of the tile (two per lane); a lane scans its run serially -- such runs are rare
+            auto val = [&](long long a) { return (a & 15) == 0 ? __ldg(rv.rs + (a >> 4)).z : __ldg(y + a); };
+            for (int i = 0; i < 2; ++i) {
+                const long long r = (t << 6) + i * 32 + lane;
+                if (r >= rv.total()) continue;
+                float rmn, rmx;
+                rv.minmax(r, rmn, rmx);
+                if (!(rmx - cmin >= min_prom)) continue;
+                const int cnt = rv.count(r);
+                for (int sidx = 0; sidx < cnt; ++sidx) {
+                    const long long k = (r << 4) + sidx;
+                    if (k < 1 || k >= V - 1) continue;
+                    const float yk = __ldg(y + k);
+                    const float prev = sidx ? __ldg(y + k - 1) : __ldg(rv.rs + r - 1).w;
+                    if (!(prev < yk) || !(yk - cmin >= min_prom)) continue;
+                    long long a = k + 1;
+                    while (a < V - 1 && val(a) == yk) ++a;          // plateau (its runs have max >= yk >= theta)
+                    if (val(a) < yk) {
+                        int slot = atomicAdd(&s_ncand, 1);
+                        if (slot < pk_cap) {
+                            p_start[slot] = (unsigned)k;
+                            p_end[slot] = (unsigned)a;
+                            p_h[slot] = yk;
+                        }
+                    }
+                }
+            }
+            continue;
+        }
         for (int it = 0; it < TP / 32; ++it) {
             long long k = k0 + it * 32 + lane;
             if (k >= 1 && k < V - 1) {
@@ -254,7 +461,7 @@ k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict_
     __syncthreads();
     int ncand = s_ncand;
     if (ncand > pk_cap) {
-        if (tid == 0) atomicOr(out.flags, 1u);
+        if (tid == 0) atomicOr(out.flags, FLAG_OVERFLOW);
         ncand = pk_cap;
     }
 
@@ -262,13 +469,24 @@ k_chunk_peaks(const float *__restrict__ c, ChunkGeom g, const float *__restrict_
     for (int i = warp; i < ncand; i += 8) {
         const float h = p_h[i];
         const long long s = p_start[i], e = p_end[i];
-        float lmin = walk_min<-1>(y, V, tmin, tmax, s, h);
-        float rmin = walk_min<+1>(y, V, tmin, tmax, e, h);
+        float lmin, rmin;
+        if constexpr (SUM) {
+            lmin = walk_min_sum<-1>(y, rv, V, tmin, tmax, s, h);
+            rmin = walk_min_sum<+1>(y, rv, V, tmin, tmax, e, h);
+        } else {
+            lmin = walk_min<-1>(y, V, tmin, tmax, s, h);
+            rmin = walk_min<+1>(y, V, tmin, tmax, e, h);
+        }
         if (lane == 0) {
             float prom = h - fmaxf(lmin, rmin);
             p_prom[i] = prom;
-            p_ld[i] = h - __ldg(y + s - 1);
-            p_rd[i] = h - __ldg(y + e);
+            if constexpr (SUM) {
+                p_ld[i] = h - ((s & 15) ? __ldg(y + s - 1) : __ldg(rv.rs + (s >> 4) - 1).w);
+                p_rd[i] = h - ((e & 15) ? __ldg(y + e) : __ldg(rv.rs + (e >> 4)).z);
+            } else {
+                p_ld[i] = h - __ldg(y + s - 1);
+                p_rd[i] = h - __ldg(y + e);
+            }
             p_alive[i] = prom >= min_prom;                          // with_min_prominence, :227
         }
     }

@@ -339,6 +339,7 @@ def _main(out_stream):
         "data": "synthetic",
         "config": {"workload": workload_name(args, wl), "fft_log2": stats["fft_log2"],
                    "four_step": f"{1 << stats['log2_n1']}x{1 << stats['log2_n2']}", "frames_per_gpu": hi - lo,
+                   "peak_pass": {0: "dense correlation", 1: "run summaries", 2: "run summaries rejected, dense repeat"}[stats["summary_mode"]],
                    "l2_policy": "inputs larger than L2 (PCM per GPU %.1f GB)" % ((hi - lo) * b_in / 1e9),
                    "n_snippets": n_snip, "snippet_hours_per_s": value * n_snip,
                    "peaks_found": len(starts), "planted": len(plan), "verified_offsets_are_planted": verified,

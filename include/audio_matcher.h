@@ -84,6 +84,8 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t fft_log2, log2_n1, log2_n2;   /* block length and its four-step split (n1 = 1 => single pass) */
     uint32_t chunks;
+    uint32_t summary_mode;      /* 0 dense correlation, 1 run summaries, 2 summaries rejected -> repeated densely */
+    uint32_t reserved;
 } am_stats;
 
 /* kernel classes for the optional per-kernel device timing */

@@ -137,6 +137,62 @@ def test_golden_case_other_block_lengths(am, orc, fft_log2):
     _assert_peaks(_run_case(am, orc, c, fft_log2=fft_log2), c["peaks"])
 
 
+@pytest.mark.parametrize("row_log2", [13, 12, 11])
+def test_summary_mode_small_cases(am, orc, row_log2):
+    """Summary mode (run records instead of the dense correlation) needs 16-column tiles, i.e. blocks of >= 2^20:
+    force that block length on the small golden cases (column lengths 128 / 256 / 512) and check the mode was used."""
+    with open(os.path.join(GOLD, "oracle_cases.json")) as f:
+        cases = json.load(f)
+    os.environ["AM_ROW_LOG2"] = str(row_log2)
+    try:
+        for c in cases:
+            pcm, snip, _ = orc.synth_case(c["sr"], c["stream_s"], c["snippet_s"], channels=c["channels"], chunk_s=c["chunk_s"],
+                                          plant_period_s=c["chunk_s"] * 2.5, plant_jitter_s=c["chunk_s"] / 2)
+            conf = am.Config(chunk_size=c["chunk_s"], overlap_length=-1.0 if c["overlap_s"] is None else c["overlap_s"],
+                             peak_config=am.PeakConfig(c["distance_s"], c["prominence"]), fft_log2=20)
+            algo = am.CudaConvolve(snip, sr=c["sr"], config=conf)
+            got = am.calc_chunks(c["sr"], pcm.reshape(-1, 2) if c["channels"] == 2 else pcm, algo, True, conf)
+            st = algo.stats()
+            algo.close()
+            _assert_peaks(got, c["peaks"])
+            # short snippets give noisy scores: a chunk minimum below theta - prominence legitimately forces the
+            # dense repeat (mode 2); the 1 s snippet case must stay in summary mode
+            assert st["summary_mode"] in (1, 2), (c["name"], st)
+            if c["name"] == "mono_16k_1s":
+                assert st["summary_mode"] == 1, st
+    finally:
+        os.environ.pop("AM_ROW_LOG2", None)
+
+
+def test_summary_mode_falls_back_to_dense(am, orc):
+    """Geometries / data the run records cannot represent exactly must be redone densely, not approximated:
+    (a) a chunk whose last run holds more than one valid output in the middle of a segment (ov = m + 4),
+    (b) a chunk minimum below theta - prominence (stream much louder than the snippet)."""
+    sr, m = 8000, 4000
+    pcm = orc.synth_pcm16(41, 0, sr * 43)
+    snip = orc.synth_pcm16(42, 0, m)
+    for k, o in enumerate([9000, 120000, 260000]):
+        orc.synth_plant(pcm, 1, snip, o, k % 2)
+    x, s = orc.pcm16_to_f32(pcm), orc.pcm16_to_f32(snip)
+    ov_s = (m + 4) / sr
+    ref = orc.calc_chunks(x, s, sr, orc.make_config(5.0, ov_s, 2.0, 0.13), scale=True, precision=64)
+    conf = am.Config(chunk_size=5.0, overlap_length=ov_s, peak_config=am.PeakConfig(2.0, 0.13), fft_log2=20)
+    algo = am.CudaConvolve(snip, sr=sr, config=conf)
+    got = am.calc_chunks(sr, pcm, algo, True, conf)
+    assert algo.stats()["summary_mode"] == 2
+    _assert_peaks(got, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+    algo.close()
+    quiet = (snip // 4).astype(np.int16)                                   # snippet 12 dB below the stream: noisy scores
+    sq = orc.pcm16_to_f32(quiet)
+    ref = orc.calc_chunks(x, sq, sr, orc.make_config(2.5, m / sr, 2.0, 0.3), scale=True, precision=64)
+    conf = am.Config(chunk_size=2.5, peak_config=am.PeakConfig(2.0, 0.3), fft_log2=20, max_peaks_per_chunk=8000)
+    algo = am.CudaConvolve(quiet, sr=sr, config=conf)
+    got = am.calc_chunks(sr, pcm, algo, True, conf)
+    assert algo.stats()["summary_mode"] == 2
+    _assert_peaks(got, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+    algo.close()
+
+
 @pytest.mark.parametrize("seed,dist,prom,maxpk", [(1, 0.0, 0.09, 8000), (2, 1.0, 0.09, 8000), (3, 3.0, 0.11, 0), (4, 480.0, 0.13, 0)])
 def test_calc_chunks_random_vs_oracle(am, orc, seed, dist, prom, maxpk):
     sr = 8000

@@ -36,9 +36,9 @@ METRIC = "audio-hours matched/sec (snippet vs stream)"
 UNIT = "audio-hours/s"
 CHUNK_S, DIST_S, PROM = 60.0, 480.0, 0.13
 # dram__bytes_read.sum + dram__bytes_write.sum per block pair at N = 2^22, from the ncu --set full capture
-# summarised in profiles/r01_ncu_full_final.csv (32-pair launches: k_row32 1.618 + 1.030 GB, k_col_fwd 0.482 + 1.020 GB,
-# k_col_inv 1.074 + 0.907 GB)
-NCU_DRAM_BYTES_PER_PAIR_2P22 = {"k_row": 82.8e6, "k_col_fwd": 46.9e6, "k_col_inv": 61.9e6}
+# summarised in profiles/r01_ncu_full_final.csv (32-pair launches: k_row32 1.574 + 1.028 GB, k_col_fwd 0.482 + 1.021 GB,
+# k_col_inv 1.074 + 0.222 GB in summary mode)
+NCU_DRAM_BYTES_PER_PAIR_2P22 = {"k_row": 81.3e6, "k_col_fwd": 47.0e6, "k_col_inv": 40.5e6}
 PLANT_PERIOD_S, PLANT_JITTER_S = 600.0, 30.0
 
 

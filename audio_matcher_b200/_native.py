@@ -78,6 +78,8 @@ SYMBOLS = {
     "am_merge_peaks": (C.c_int, [C.POINTER(AmPeak), _SZ, C.c_uint32, C.c_double, C.POINTER(AmPeak), _SZ,
                                  C.POINTER(_SZ)]),
     "am_is_overshadowed": (C.c_int, [C.POINTER(AmPeak), C.POINTER(AmPeak), C.c_uint32, C.c_double]),
+    "am_debug_peaks_from_correlation": (C.c_int, [_VP, _VP, _SZ, C.c_int, C.POINTER(AmPeak), _SZ, C.POINTER(_SZ),
+                                                  C.POINTER(C.c_uint32)]),
     "am_synth_pcm16_device": (C.c_int, [C.c_uint64, C.c_uint64, _SZ, _VP, _VP]),
     "am_synth_plant_device": (C.c_int, [_VP, _SZ, C.c_int, _VP, _SZ, C.c_uint64, C.c_int, _VP]),
 }

@@ -913,6 +913,83 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     return AM_OK;
 }
 
+
+// Test hook (tests/test_gpu_parity.py): run the per-chunk peak kernels on a correlation supplied by the caller
+// instead of one computed from a stream.  `c_host` holds the n outputs of one segment that starts at chunk 0; the
+// chunk geometry comes from the matcher's config and snippet length.  summary != 0 exercises the run-record path
+// (records built from c, runs below theta poisoned with NaN); peaks come back before the global filter.
+am_status am_debug_peaks_from_correlation(am_matcher *h, const float *c_host, size_t n, int summary, am_peak *out,
+                                          size_t cap, size_t *n_out, uint32_t *mode_out) {
+    if (!h || !c_host || !n_out || n == 0) return fail(AM_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    long long C, ov;
+    chunk_params(h, C, ov);
+    const long long m = (long long)h->m, L = (long long)n + m - 1;
+    if (C <= 0 || C + ov >= (1ll << 31)) return fail(AM_ERR_INVALID, "bad chunk geometry");
+    if (summary && (C % 16) != 0) return fail(AM_ERR_INVALID, "summary mode needs a chunk size that is a multiple of 16 samples");
+    const long long nchunks = (L + C - 1) / C;
+    const long long seg_c_len = (((long long)n + 15) / 16) * 16;
+    TRY(h->d_c.reserve((size_t)seg_c_len));
+    TRY(h->d_rsum.reserve((size_t)seg_c_len >> 4));
+    const long long tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
+    TRY(h->d_tmin.reserve((size_t)(nchunks * tiles_stride)));
+    TRY(h->d_tmax.reserve((size_t)(nchunks * tiles_stride)));
+    const int pk_cap = h->cfg.max_peaks_per_chunk ? (int)h->cfg.max_peaks_per_chunk : 1024;
+    size_t pk_smem = (size_t)pk_cap * (2 * sizeof(unsigned) + 4 * sizeof(float) + 1);
+    int sm_tiles = 0;
+    if (pk_smem + (size_t)tiles_stride * 8 <= 96 * 1024) sm_tiles = (int)tiles_stride;
+    pk_smem += (size_t)sm_tiles * 8;
+    if (pk_smem > 200 * 1024) return fail(AM_ERR_INVALID, "max_peaks_per_chunk too large");
+    TRY(set_smem(amp::k_chunk_peaks<false>, pk_smem));
+    TRY(set_smem(amp::k_chunk_peaks<true>, pk_smem));
+    const size_t dev_cap = std::min<size_t>((size_t)nchunks * (size_t)pk_cap, (size_t)1 << 22);
+    TRY(h->d_peaks.reserve(dev_cap));
+    amp::PeakOut po;
+    po.peaks = h->d_peaks.p; po.cap = dev_cap; po.count = h->d_count.p; po.flags = (unsigned *)(h->d_count.p + 1);
+    const unsigned long long min_dist = (unsigned long long)h->cfg.distance_s * (unsigned long long)h->sr;
+    const float theta = 0.5f * h->cfg.prominence;
+    amp::ChunkGeom cg;
+    cg.C = C; cg.ov = ov; cg.m = m; cg.total = L; cg.first_chunk = 0; cg.c_g0 = 0; cg.tiles_stride = (int)tiles_stride;
+    cg.c_stride = seg_c_len; cg.seg_end = (long long)n;
+    dim3 tgrid3((unsigned)((tiles_stride + 7) / 8), (unsigned)nchunks, 1), pgrid((unsigned)nchunks, 1);
+    unsigned long long cnt[2] = {0, 0};
+    uint32_t mode = summary ? 1 : 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool sum = summary && pass == 0;
+        if (pass == 1 && !(summary && ((unsigned)cnt[1] & amp::FLAG_NEED_DENSE))) break;
+        if (pass == 1) mode = 2;
+        CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
+        CU(cudaMemcpyAsync(h->d_c.p, c_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        if (sum) {
+            amp::k_debug_make_runs<<<(unsigned)(((seg_c_len >> 4) + 255) / 256), 256, 0, h->stream>>>(h->d_c.p, (long long)n, theta, h->d_rsum.p);
+            amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(h->d_rsum.p, cg, h->d_tmin.p, h->d_tmax.p, po.flags);
+            amp::k_chunk_peaks<true><<<pgrid, 256, pk_smem, h->stream>>>(h->d_c.p, h->d_rsum.p, theta, cg, h->d_tmin.p, h->d_tmax.p,
+                                                                       h->cfg.prominence, min_dist, pk_cap, sm_tiles, po);
+        } else {
+            amp::k_tile_minmax<<<tgrid3, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p);
+            amp::k_chunk_peaks<false><<<pgrid, 256, pk_smem, h->stream>>>(h->d_c.p, nullptr, 0.f, cg, h->d_tmin.p, h->d_tmax.p,
+                                                                        h->cfg.prominence, min_dist, pk_cap, sm_tiles, po);
+        }
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(cnt, h->d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    if (mode_out) *mode_out = mode;
+    if ((unsigned)cnt[1] & amp::FLAG_OVERFLOW) return fail(AM_ERR_CAPACITY, "more than max_peaks_per_chunk = %d candidates in a chunk", pk_cap);
+    if (cnt[0] > dev_cap) return fail(AM_ERR_CAPACITY, "%llu peaks exceed the device list capacity %zu", cnt[0], dev_cap);
+    std::vector<am_peak> all((size_t)cnt[0]);
+    if (cnt[0]) CU(cudaMemcpy(all.data(), h->d_peaks.p, (size_t)cnt[0] * sizeof(am_peak), cudaMemcpyDeviceToHost));
+    std::stable_sort(all.begin(), all.end(), [](const am_peak &a, const am_peak &b) {
+        if (a.chunk != b.chunk) return a.chunk < b.chunk;
+        return a.height > b.height || (a.height == b.height && a.start < b.start);
+    });
+    *n_out = all.size();
+    if (all.size() > cap) return fail(AM_ERR_CAPACITY, "%zu peaks, capacity %zu", all.size(), cap);
+    if (!all.empty()) memcpy(out, all.data(), all.size() * sizeof(am_peak));
+    return AM_OK;
+}
+
 am_status am_calc_chunks(am_matcher *h, const void *stream, size_t frames, am_sample_fmt fmt, am_mem mem, int scale,
                          am_peak *out, size_t cap, size_t *n_out) {
     return am_calc_chunks_range(h, stream, 0, frames, frames, fmt, mem, scale, 0, (size_t)-1, 1, out, cap, n_out);

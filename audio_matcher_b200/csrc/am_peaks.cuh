@@ -555,4 +555,20 @@ k_chunk_peaks(const float *__restrict__ c, const float4 *__restrict__ rsum, floa
     }
 }
 
+// Test hook: build the run records the summary epilogue of k_col_inv would have written for a correlation that is
+// already in memory, and poison (NaN) every run it would not have stored, so that any read the summary-mode
+// kernels are not entitled to shows up as a wrong result.
+__global__ void k_debug_make_runs(float *__restrict__ c, long long n, float theta, float4 *__restrict__ rsum) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if ((r << 4) >= n) return;
+    const long long left = n - (r << 4);
+    const int valid = left < 16 ? (int)left : 16;
+    float *p = c + (r << 4);
+    float mn = p[0], mx = p[0], last = p[0];
+    for (int i = 1; i < valid; ++i) { mn = fminf(mn, p[i]); mx = fmaxf(mx, p[i]); last = p[i]; }
+    rsum[r] = make_float4(mn, mx, p[0], last);
+    if (!(mx >= theta))
+        for (int i = 0; i < valid; ++i) p[i] = __int_as_float(0x7fc00000);
+}
+
 }  // namespace amp

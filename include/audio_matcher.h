@@ -174,6 +174,13 @@ am_status am_merge_peaks(am_peak *peaks, size_t n, uint32_t sr, double distance_
 /* is_overshadowed (audio_matcher.rs:143-160); other == NULL is None */
 int am_is_overshadowed(const am_peak *element, const am_peak *other, uint32_t sr, double max_distance_s);
 
+/* Test hook: the per-chunk peak kernels on a caller-supplied correlation (one segment starting at chunk 0, chunk
+ * geometry from the matcher's config and snippet length).  summary != 0 uses the run-record path with every run the
+ * transform kernels would not have stored poisoned; *mode_out: 0 dense, 1 run records, 2 records rejected -> dense.
+ * Peaks are returned before the global sort / neighbour filter, ordered by (chunk, height descending). */
+am_status am_debug_peaks_from_correlation(am_matcher *h, const float *c_host, size_t n, int summary, am_peak *out,
+                                          size_t cap, size_t *n_out, uint32_t *mode_out);
+
 /* ---- synthetic workload generator (bench/test utility) -------------------
  * Device-side, integer-only, bit-identical to the oracle's generator.
  * out[i] = int16((hash64(seed, first + i) >> 50) - 8192) */

@@ -262,6 +262,80 @@ def test_batch_equals_independent_runs(am, orc):
     batch.close()
 
 
+def _peaks_from_correlation(am, native, c, m, C_, ov, prom, dist, summary, maxpk=0):
+    """tests-only hook: per-chunk peak kernels on a supplied correlation (sr = 1, so seconds == samples)."""
+    conf = am.Config(chunk_size=float(C_), overlap_length=float(ov), peak_config=am.PeakConfig(float(dist), prom),
+                     max_peaks_per_chunk=maxpk)
+    algo = am.CudaConvolve(np.ones(m, np.float32), sr=1, config=conf)
+    c = np.ascontiguousarray(c, np.float32)
+    cap = c.size // 2 + 8
+    buf = (native.AmPeak * cap)()
+    got, mode = C.c_size_t(), C.c_uint32()
+    native.check(native.lib().am_debug_peaks_from_correlation(algo._h, c.ctypes.data, c.size, int(summary), buf, cap,
+                                                              C.byref(got), C.byref(mode)))
+    algo.close()
+    return [(buf[i].chunk, buf[i].start, buf[i].end, buf[i].height, buf[i].prominence, buf[i].left_diff, buf[i].right_diff)
+            for i in range(got.value)], mode.value
+
+
+def _oracle_peaks_from_correlation(orc, c, m, C_, ov, prom, dist):
+    L = c.size + m - 1
+    out = []
+    for i in range((L + C_ - 1) // C_):
+        n = min(C_ + ov, L - C_ * i)
+        if n < m:
+            continue
+        y = c[C_ * i: C_ * i + n - m + 1]
+        for p in orc.find_peaks(y, prom, dist):
+            out.append((i, p.start + C_ * i, p.end + C_ * i, p.height, p.prominence, p.left_diff, p.right_diff))
+    return out
+
+
+@pytest.mark.parametrize("summary", [0, 1])
+@pytest.mark.parametrize("seed", range(6))
+def test_peak_kernels_on_adversarial_correlations(am, orc, native, seed, summary):
+    """The peak kernels (dense and run-record paths) against the oracle's find_peaks on arrays no transform would
+    produce: heavy quantisation (plateaus inside runs, across run and tile boundaries), peaks next to chunk edges,
+    flat and monotone stretches.  Everything must match bit for bit; in summary mode unstored runs are poisoned."""
+    rng = np.random.default_rng(100 + seed)
+    C_, m = 4096, 37
+    ov = [m, m - 1, m + 15, m, m + 31, m][seed]                      # V = C+1, C, C+16, C+1, C+32, C+1 (partial runs of 0/1 outputs)
+    n = 5 * C_ + [1, 0, 16, 777, 32, 2049][seed]
+    levels = [4, 9, 33, 3, 17, 65][seed]
+    c = np.round(rng.random(n) * levels) / levels * 0.2 - 0.02       # quantised noise in [-0.02, 0.18]: many plateaus
+    for pos in rng.integers(2, n - 2, size=40):                      # bumps of various widths and heights
+        w = int(rng.integers(1, 40))
+        c[pos:pos + w] = np.maximum(c[pos:pos + w], rng.choice([0.3, 0.5, 0.5, 0.8, 1.0]))
+    c[1] = 0.9; c[C_ - 1] = 0.95; c[C_] = 0.95; c[C_ + 1] = 0.7       # next to array / chunk edges, plateau over a chunk boundary
+    c[2 * C_ + 15:2 * C_ + 17] = 0.6                                  # plateau across a run boundary
+    c[3 * C_ + 1023:3 * C_ + 1026] = 0.65                             # plateau across a tile boundary
+    c[4 * C_:4 * C_ + 300] = np.linspace(0.0, 0.17, 300)              # monotone stretch
+    c = c.astype(np.float32)
+    for prom, dist in ((0.13, 0), (0.25, 100), (0.13, 3000)):
+        ref = _oracle_peaks_from_correlation(orc, c, m, C_, ov, prom, dist)
+        got, mode = _peaks_from_correlation(am, native, c, m, C_, ov, prom, dist, summary, maxpk=4000)
+        assert mode == (1 if summary else 0)
+        assert len(ref) > 5
+        assert sorted(got) == sorted(ref)
+
+
+def test_peak_kernels_summary_rejections(am, orc, native):
+    """Run records cannot represent (a) a partial last run with more than one output inside a segment and (b) a chunk
+    minimum below theta - prominence: both must come back as mode 2 (dense repeat) with exact results."""
+    rng = np.random.default_rng(7)
+    C_, m = 4096, 37
+    c = (rng.random(3 * C_ + 5) * 0.1).astype(np.float32)
+    c[[500, 5000, 9000]] = [1.0, 0.6, 0.8]
+    ref = _oracle_peaks_from_correlation(orc, c, m, C_, m + 4, 0.13, 0)
+    got, mode = _peaks_from_correlation(am, native, c, m, C_, m + 4, 0.13, 0, 1)           # V = C + 5
+    assert mode == 2 and sorted(got) == sorted(ref)
+    c2 = c.copy()
+    c2[7000] = -0.5                                                                          # chunk minimum far below -prom/2
+    ref = _oracle_peaks_from_correlation(orc, c2, m, C_, m, 0.13, 0)
+    got, mode = _peaks_from_correlation(am, native, c2, m, C_, m, 0.13, 0, 1, maxpk=4000)
+    assert mode == 2 and sorted(got) == sorted(ref)
+
+
 def test_edge_cases(am, orc, native):
     sr = 8000
     snip = orc.synth_pcm16(7, 0, 4000)

@@ -332,6 +332,14 @@ def _main(out_stream):
         cpu_baseline = {"value": (chunks * CHUNK_S / 3600.0) / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{chunks} logical chunks ({chunks * CHUNK_S:.0f} s of audio) of this workload, "
                                   f"exact-length f32 FFTs per chunk like the reference, {dt:.1f} s wall"}
+        # second CPU line: same semantics with power-of-two transforms and a cached snippet spectrum,
+        # so the comparison is not inflated by the reference's exact-length transforms
+        t = time.perf_counter()
+        orc.calc_chunks(x, s, sr, orc.make_config(CHUNK_S, len(s) / sr, DIST_S, PROM), scale=True, precision=33,
+                        threads=cores, n_chunks=chunks)
+        dt2 = time.perf_counter() - t
+        cpu_baseline["optimised_port"] = {"value": (chunks * CHUNK_S / 3600.0) / dt2, "unit": UNIT, "cores": cores,
+                                          "note": f"power-of-two f32 FFTs + cached snippet spectrum, same sample, {dt2:.1f} s wall"}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

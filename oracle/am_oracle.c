@@ -156,6 +156,41 @@ int orc_correlate_direct(const float *within, size_t n, const float *sample, siz
     return 0;
 }
 
+
+/* "Optimised CPU" variant for the baseline discussion (second CPU line): same semantics as
+ * orc_correlate_f but with power-of-two transforms and a snippet spectrum computed once, so that the GPU speed-up
+ * is not inflated by the reference's exact-length (often prime) transforms and per-chunk snippet FFT
+ * (audio_matcher.rs:305).  Valid mode only. */
+typedef struct { size_t N; cpx_f *spec; plan_f *plan; } orc_pow2_cache;
+
+static orc_pow2_cache *pow2_cache_new(const float *sample, size_t m, size_t N) {
+    orc_pow2_cache *c = (orc_pow2_cache *)calloc(1, sizeof *c);
+    c->N = N;
+    c->plan = plan_new_f(N);
+    c->spec = (cpx_f *)calloc(N, sizeof(cpx_f));
+    cpx_f *w = (cpx_f *)malloc(2 * N * sizeof(cpx_f));
+    for (size_t j = 0; j < m; ++j) c->spec[j].re = sample[j];
+    fft_any_f(c->plan, c->spec, 0, w);
+    for (size_t k = 0; k < N; ++k) c->spec[k].im = -c->spec[k].im;       /* conj: correlation */
+    free(w);
+    return c;
+}
+static void pow2_cache_free(orc_pow2_cache *c) {
+    if (!c) return;
+    plan_free_f(c->plan); free(c->spec); free(c);
+}
+static void correlate_pow2_valid(const orc_pow2_cache *c, const float *within, size_t n, size_t m, float *out) {
+    size_t N = c->N, V = n - m + 1;
+    cpx_f *a = (cpx_f *)calloc(N, sizeof(cpx_f)), *w = (cpx_f *)malloc(2 * N * sizeof(cpx_f));
+    for (size_t i = 0; i < n; ++i) a[i].re = within[i];
+    fft_any_f(c->plan, a, 0, w);
+    for (size_t k = 0; k < N; ++k) a[k] = cmul_f(a[k], c->spec[k]);
+    fft_any_f(c->plan, a, 1, w);
+    float inv = (float)(1.0 / (double)N);
+    for (size_t k = 0; k < V; ++k) out[k] = a[k].re * inv;               /* N >= n + m - 1: no wrap-around */
+    free(a); free(w);
+}
+
 /* inverse_sample_auto_correlation: audio_matcher.rs:321-329
  * 1 / fftcorrelate(sample, sample, Valid)[0]  (f32 transform like the reference) */
 float orc_inv_autocorr_f32(const float *sample, size_t m) {
@@ -302,6 +337,13 @@ size_t orc_calc_chunks_range(const float *stream, size_t L, const float *snippet
     float inv_ac = 1.0f;
     if (scale) inv_ac = (precision == 32) ? orc_inv_autocorr_f32(snippet, m)
                                           : (float)orc_inv_autocorr_exact(snippet, m);
+    /* precision 33: "optimised CPU" -- power-of-two f32 transforms, snippet spectrum cached for full windows */
+    orc_pow2_cache *pcache = NULL;
+    if (precision == 33) {
+        size_t N = 1;
+        while (N < C + ov + m - 1) N <<= 1;
+        pcache = pow2_cache_new(snippet, m, N);
+    }
 
     orc_peak **lists = (orc_peak **)calloc(num_chunks, sizeof(orc_peak *));
     size_t *counts = (size_t *)calloc(num_chunks, sizeof(size_t));
@@ -318,6 +360,8 @@ size_t orc_calc_chunks_range(const float *stream, size_t L, const float *snippet
         float *c = (float *)malloc(V * sizeof(float));
         if (precision == 32) {
             orc_correlate_f(stream + offset, n, snippet, m, ORC_MODE_VALID, c);
+        } else if (precision == 33) {
+            correlate_pow2_valid(pcache, stream + offset, n, m, c);          /* short tail windows reuse the big plan */
         } else {
             double *cd = (double *)malloc(V * sizeof(double));
             if (precision == 64) {
@@ -352,6 +396,7 @@ size_t orc_calc_chunks_range(const float *stream, size_t L, const float *snippet
         free(lists[ci]);
     }
     free(lists); free(counts);
+    pow2_cache_free(pcache);
     size_t nout = 0;
     if (!final_filter) {
         for (size_t k = 0; k < tot; ++k) { if (nout < cap) out[nout] = all[k]; ++nout; }

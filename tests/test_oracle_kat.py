@@ -142,6 +142,18 @@ def test_golden_oracle_cases_reproduce(orc):
             assert np.allclose([p.height for p in got], [p[2] for p in c["peaks"]], rtol=1e-4)
 
 
+def test_optimised_cpu_variant_matches(orc):
+    """precision 33 (power-of-two transforms, cached snippet spectrum: the 'optimised CPU' baseline line) must find
+    the same peaks as the exact-length restatement."""
+    pcm, snip, _ = orc.synth_case(8000, 47.0, 1.0, chunk_s=5.0, plant_period_s=12.5, plant_jitter_s=2.5)
+    x, s = orc.pcm16_to_f32(pcm), orc.pcm16_to_f32(snip)
+    cfg = orc.make_config(5.0, 1.0, 2.0, 0.13)
+    a = orc.calc_chunks(x, s, 8000, cfg, precision=32)
+    b = orc.calc_chunks(x, s, 8000, cfg, precision=33)
+    assert len(a) >= 3 and [p.start for p in a] == [p.start for p in b]
+    assert np.allclose([p.height for p in a], [p.height for p in b], rtol=1e-4)
+
+
 def test_sharded_oracle_equals_whole(orc):
     pcm, snip, _ = orc.synth_case(8000, 60.0, 0.5, chunk_s=5.0, plant_period_s=12.5, plant_jitter_s=2.5)
     x, s = orc.pcm16_to_f32(pcm), orc.pcm16_to_f32(snip)

@@ -18,6 +18,8 @@
 #include <new>
 #include <vector>
 
+#include <cuda.h>
+
 #include "../../include/audio_matcher.h"
 #include "am_kernels.cuh"
 #include "am_peaks.cuh"
@@ -100,6 +102,7 @@ struct am_matcher {
     std::vector<double> sumsq;
     std::vector<float> inv_ac;
     DevBuf<float2> d_tw;
+    DevBuf<int> d_sched;                // next-tile counter of the persistent kernels
     std::map<int, float2 *> spectra;         // log2n -> [S][N] conjugate spectra
     DevBuf<float2> d_A, d_B;
     DevBuf<float> d_c, d_tmin, d_tmax;
@@ -183,6 +186,68 @@ am_status launch_small(am_matcher *h, int log2n, const amk::BlockGroup &g, const
     return fail(AM_ERR_UNSUPPORTED, "single-pass length 2^%d not built", log2n);
 }
 
+// TMA descriptor over a resident mono int16 window: rows of N2 frames at a pitch of N2 frames, 2 N2 columns wide (see
+// k_col_fwd_stream).  The driver entry point is looked up once; false = not available (the caller keeps the LDG kernel).
+typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_t tensor_map_encoder() {
+    static const encode_t encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        cudaGetLastError();
+        return (encode_t)fn;
+    }();
+    return encode;
+}
+static_assert(sizeof(amk::TensorMap) == sizeof(CUtensorMap), "tensor map size");
+bool encode_pcm_tensor_map(amk::TensorMap *out, const amk::StreamView &sv, int log2n2, int box_cols, int box_rows, int frame_bytes) {
+    const encode_t encode = tensor_map_encoder();
+    if (!encode || (((size_t)sv.x) & 15) != 0 || sv.buf_frames < (1ll << log2n2)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)2 << log2n2, (cuuint64_t)(sv.buf_frames >> log2n2) + 1};
+    const cuuint64_t strides[1] = {(cuuint64_t)frame_bytes << log2n2};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+    return encode((CUtensorMap *)out, frame_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
+                  const_cast<void *>(sv.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_64B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// true = launched; false with last_status() == AM_OK = not applicable (the caller falls back to k_col_fwd)
+thread_local am_status tl_status = AM_OK;
+am_status last_status() { return tl_status; }
+template <int L1, int LT, int E, int FMT>
+bool launch_col_stream(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *A, dim3 grid) {
+    typedef amk::ColStreamCfg<L1, LT, E, FMT> SC;
+    tl_status = AM_OK;
+    if constexpr (!SC::OK) return false;
+    else {
+        amk::TensorMap tm;
+        if (!encode_pcm_tensor_map(&tm, g.sv, l2, SC::T, SC::BOX_ROWS, (int)sizeof(typename SC::Frame))) return false;
+        static const int ctas = [] {
+            const char *v = getenv("AM_COL_STREAM_CTAS");
+            if (v && *v) return atoi(v);
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(amk::k_col_fwd_stream<L1, LT, E, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC::SMEM);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amk::k_col_fwd_stream<L1, LT, E, FMT>, SC::THREADS, SC::SMEM);
+            return sms * (per_sm > 0 ? per_sm : 1);
+        }();
+        const int ntiles = (int)(grid.x * grid.y), nctas = ntiles < ctas ? ntiles : ctas;
+        auto body = [&]() -> am_status {
+            TRY(set_smem(amk::k_col_fwd_stream<L1, LT, E, FMT>, SC::SMEM));
+            TRY(h->d_sched.reserve(1));
+            CU(cudaMemsetAsync(h->d_sched.p, 0, sizeof(int), h->stream));
+            LAUNCH(h, AM_K_COL_FWD, amk::k_col_fwd_stream<L1, LT, E, FMT><<<nctas, SC::THREADS, SC::SMEM, h->stream>>>(tm, g, l2, A, h->d_tw.p, ntiles, h->d_sched.p));
+            return AM_OK;
+        };
+        tl_status = body();
+        return tl_status == AM_OK;
+    }
+}
+
 template <int L1, int LT, int E, bool INV> am_status launch_col_t(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *A) {
     typedef amk::ColCfg<L1, LT, E> Cfg;
     int pairs = (g.nblocks + 1) / 2;
@@ -191,6 +256,16 @@ template <int L1, int LT, int E, bool INV> am_status launch_col_t(am_matcher *h,
         TRY(set_smem(amk::k_col_inv<L1, LT, E>, Cfg::SMEM_INV));
         LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT, E><<<grid, Cfg::THREADS, Cfg::SMEM_INV, h->stream>>>(g, l2, A, h->d_tw.p));
     } else {
+        // resident window in one of the three sample formats: persistent kernel whose next tile is fetched by TMA
+        static const bool stream_on = [] { const char *v = getenv("AM_COL_STREAM"); return !(v && *v == '0'); }();
+        if (stream_on) {
+            switch (g.sv.fmt) {
+            case amk::FMT_I16_MONO: if (launch_col_stream<L1, LT, E, amk::FMT_I16_MONO>(h, g, l2, A, grid)) return AM_OK; break;
+            case amk::FMT_I16_STEREO: if (launch_col_stream<L1, LT, E, amk::FMT_I16_STEREO>(h, g, l2, A, grid)) return AM_OK; break;
+            case amk::FMT_F32_MONO: if (launch_col_stream<L1, LT, E, amk::FMT_F32_MONO>(h, g, l2, A, grid)) return AM_OK; break;
+            }
+            if (last_status() != AM_OK) return last_status();
+        }
         TRY(set_smem(amk::k_col_fwd<L1, LT, E>, Cfg::SMEM));
         LAUNCH(h, AM_K_COL_FWD, amk::k_col_fwd<L1, LT, E><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(g, l2, A, h->d_tw.p));
     }
@@ -202,6 +277,7 @@ template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::Block
     // tiles (one exchange, 80 registers, 3 CTAs per SM) -- measured; AM_COL_EPT_FWD / AM_COL_EPT_INV override
     static const int ept_fwd = [] { const char *v = getenv("AM_COL_EPT_FWD"); return v && *v ? atoi(v) : 16; }();
     static const int ept_inv = [] { const char *v = getenv("AM_COL_EPT_INV"); return v && *v ? atoi(v) : 32; }();
+    static const bool ept_fwd_set = [] { const char *v = getenv("AM_COL_EPT_FWD"); return v && *v; }();
     const int ept = INV ? ept_inv : ept_fwd;
     switch (l1) {
 #define C_(L) case L: return launch_col_t<L, amk::col_default_lt(L), 16, INV>(h, g, l2, A);
@@ -211,6 +287,8 @@ template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::Block
         if (lt_env == 5) return launch_col_t<8, 5, 16, INV>(h, g, l2, A);
         return launch_col_t<8, 4, 16, INV>(h, g, l2, A);
     case 9:                                   // tuning knobs: 8 or 16 columns per tile, 16 or 32 elements per thread
+        // forward tiles take the TMA-fed persistent kernel, which is fastest with 32 elements per thread
+        if (!INV && !ept_fwd_set) return launch_col_t<9, 4, 32, INV>(h, g, l2, A);
         if (ept == 32) return launch_col_t<9, 4, 32, INV>(h, g, l2, A);
         if (lt_env == 3) return launch_col_t<9, 3, 16, INV>(h, g, l2, A);
         return launch_col_t<9, 4, 16, INV>(h, g, l2, A);
@@ -241,6 +319,25 @@ am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, 
     if constexpr (L2 == 13) {
         if (ept == 32) {
             typedef amk::Row32Cfg<L2> C32;
+            if constexpr (MODE == amk::ROW_FUSED) {
+                // persistent kernel fed by bulk asynchronous copies (AM_ROW_STREAM=0: off)
+                static const bool stream_on = [] { const char *v = getenv("AM_ROW_STREAM"); return !(v && *v == '0'); }();
+                if (stream_on) {
+                    static const int ctas = [] {
+                        const char *v = getenv("AM_ROW_STREAM_CTAS");
+                        if (v && *v) return atoi(v);
+                        int dev = 0, sms = 0;
+                        cudaGetDevice(&dev);
+                        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                        return sms * 2;
+                    }();
+                    TRY(set_smem(amk::k_row32_stream<L2>, C32::SMEM));
+                    TRY(h->d_sched.reserve(1));
+                    CU(cudaMemsetAsync(h->d_sched.p, 0, sizeof(int), h->stream));
+                    LAUNCH(h, AM_K_ROW, amk::k_row32_stream<L2><<<rows < ctas ? rows : ctas, C32::THREADS, C32::SMEM, h->stream>>>(A, spec, l1, rows, h->d_tw.p, h->d_sched.p));
+                    return AM_OK;
+                }
+            }
             TRY(set_smem(amk::k_row32<L2, MODE>, C32::SMEM));
             LAUNCH(h, AM_K_ROW, amk::k_row32<L2, MODE><<<rows, C32::THREADS, C32::SMEM, h->stream>>>(A, spec, B, l1, rows, h->d_tw.p));
             return AM_OK;
@@ -589,7 +686,7 @@ void am_matcher_destroy(am_matcher *h) {
     cudaDeviceSynchronize();
     for (auto &kv : h->spectra) cudaFree(kv.second);
     h->d_snip.release(); h->d_tw.release(); h->d_A.release(); h->d_B.release(); h->d_c.release(); h->d_tmin.release();
-    h->d_tmax.release(); h->d_rsum.release(); h->d_peaks.release(); h->d_count.release();
+    h->d_tmax.release(); h->d_rsum.release(); h->d_peaks.release(); h->d_count.release(); h->d_sched.release();
     h->d_stage[0].release(); h->d_stage[1].release();
     for (int i = 0; i < 2; ++i) {
         if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);

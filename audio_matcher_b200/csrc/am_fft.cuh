@@ -21,6 +21,13 @@
 #define AM_HD __host__ __device__ __forceinline__
 #endif
 
+// AM_TL(i): per-CTA phase timestamps for the micro-benchmarks under build/mb (compiled out of the library)
+#ifndef AM_TL
+#define AM_TL(i)
+#define AM_TL_SET(tile)
+#define AM_TL_WAIT(v, n)
+#endif
+
 namespace amfft {
 
 constexpr int EPT = 16;           // complex elements per thread
@@ -271,12 +278,30 @@ template <int LOG2N, int LOG2B, bool INV, int E = EPT> struct RegFFT {
     template <int ST = 0> static __device__ __forceinline__ void run(float2 (&v)[EPT], float2 *sm, int gtid,
                                                                      const float2 *__restrict__ tw) {
         butterfly<ST>(v, gtid, tw);
+        AM_TL(8 + (INV ? 9 : 0) + ST * 3);
+        if constexpr (ST + 1 < NST) {
+            xchg_write<ST>(v, sm, gtid);
+            __syncthreads();
+            AM_TL(8 + (INV ? 9 : 0) + ST * 3 + 1);
+            xchg_read<ST + 1>(v, sm, gtid);
+            __syncthreads();
+            AM_TL(8 + (INV ? 9 : 0) + ST * 3 + 2);
+            run<ST + 1>(v, sm, gtid, tw);
+        }
+    }
+    // Same, calling hook() once when the exchange buffer has been read for the last time (before the last stage's
+    // butterflies): from there on the buffer is free, e.g. as the landing zone of an asynchronous copy.
+    template <int ST = 0, class Hook>
+    static __device__ __forceinline__ void run_hook(float2 (&v)[EPT], float2 *sm, int gtid, const float2 *__restrict__ tw,
+                                                    Hook &&hook) {
+        if constexpr (ST + 1 == NST) hook();
+        butterfly<ST>(v, gtid, tw);
         if constexpr (ST + 1 < NST) {
             xchg_write<ST>(v, sm, gtid);
             __syncthreads();
             xchg_read<ST + 1>(v, sm, gtid);
             __syncthreads();
-            run<ST + 1>(v, sm, gtid, tw);
+            run_hook<ST + 1>(v, sm, gtid, tw, hook);
         }
     }
 #endif

@@ -211,6 +211,20 @@ __device__ __forceinline__ void load_tile_fast(float2 (&v)[F::EPT], const BlockG
 // blocks are interleaved as (re, im) int16 pairs in one 32-bit word per element, and the threads then
 // pick their stage-0 inputs with conflict-free LDS.32.  Needs 16-byte aligned rows (block advance V_N
 // and segment starts multiples of 8 frames), which the host arranges; anything else takes the scalar path.
+#ifndef AM_X_L2HINT
+#define AM_X_L2HINT 0
+#endif
+__device__ __forceinline__ uint4 ldg_tile16(const void *p) {
+    uint4 r;
+#if AM_X_L2HINT == 128
+    asm volatile("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#elif AM_X_L2HINT == 256
+    asm volatile("ld.global.nc.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#else
+    r = __ldg((const uint4 *)p);
+#endif
+    return r;
+}
 template <class F, int LT, int L1, int THREADS>
 __device__ __forceinline__ void load_tile_i16_staged(float2 (&v)[F::EPT], const BlockGroup &g, long long f0, int log2n2,
                                                       int tid, unsigned *sraw) {
@@ -220,8 +234,8 @@ __device__ __forceinline__ void load_tile_i16_staged(float2 (&v)[F::EPT], const 
     for (int u = tid; u < (2 << L1); u += THREADS) {
         const int n1 = u >> 1, half = u & 1;
         const short *p = x + ((long long)n1 << log2n2) + half * 8;
-        const uint4 re = __ldg((const uint4 *)p);
-        const uint4 im = __ldg((const uint4 *)(p + g.VN));
+        const uint4 re = ldg_tile16(p);
+        const uint4 im = ldg_tile16(p + g.VN);
         uint4 a, b;
         a.x = __byte_perm(re.x, im.x, 0x5410); a.y = __byte_perm(re.x, im.x, 0x7632);
         a.z = __byte_perm(re.y, im.y, 0x5410); a.w = __byte_perm(re.y, im.y, 0x7632);
@@ -244,6 +258,65 @@ __device__ __forceinline__ void load_tile_i16_staged(float2 (&v)[F::EPT], const 
     __syncthreads();                                            // the buffer becomes the exchange buffer
 }
 
+// v[l * R + s] *= base * step^(l + NB * s): the thread's E = NB * R outputs k1 = q + (N1 / E) (l + NB s) form one
+// geometric sequence (two sincospif per thread instead of two per radix-R group)
+template <int R, int NB> __device__ __forceinline__ void twiddle_geo_all(float2 *v, float2 base, float2 step) {
+    using amfft::cmul;
+    constexpr int E = R * NB;
+    float2 w[E];
+    w[0] = base;
+    w[1] = cmul(base, step);
+    float2 sp = step;
+#pragma unroll
+    for (int h = 2; h < E; h <<= 1) {
+        sp = cmul(sp, sp);                         // step^h
+#pragma unroll
+        for (int i = 0; i < h; ++i) w[h + i] = cmul(w[i], sp);
+    }
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const int e = (i % NB) * R + i / NB;
+        v[e] = cmul(v[e], w[i]);
+    }
+}
+
+// column transform of one tile held in registers, four-step twiddle, store to A[pair][k1][n2]
+template <int L1, int LT, int E>
+__device__ __forceinline__ void col_fwd_finish(float2 (&v)[E], float2 *sm_all, int tid, const float2 *__restrict__ tw,
+                                               int log2n2, int n2_0, float2 *__restrict__ Ap) {
+    typedef RegFFT<L1, LT, false, E> F;
+#ifndef AM_X_NOFFT
+    F::run(v, sm_all, tid, tw);
+#endif
+    AM_TL(2);
+    const float two_over_n = 2.0f / (float)(1u << (L1 + log2n2));
+    constexpr int RB = F::bits_at(F::NST - 1), R = 1 << RB, NB = E / R;
+    const int t = tid & ((1 << LT) - 1), q = tid >> LT;      // q < N1 / E
+    const unsigned n2 = n2_0 + t;
+#ifndef AM_X_NOTWIDDLE
+#ifdef AM_X_GEOALL
+    // k1 = q + (N1 / E) (l + NB s)
+    twiddle_geo_all<R, NB>(v, twiddle_big(n2 * (unsigned)q, two_over_n, false),
+                           twiddle_big(n2 << (L1 - RB - (NB == 1 ? 0 : (NB == 2 ? 1 : 2))), two_over_n, false));
+#else
+#pragma unroll
+    for (int l = 0; l < NB; ++l)       // k1 = q_l + s (N1 / R): W_N^{n2 k1} = W_N^{n2 q_l} (W_N^{n2 N1 / R})^s
+        twiddle_geo<R>(&v[l * R], twiddle_big(n2 * (unsigned)(q + l * (F::GT >> LT)), two_over_n, false),
+                       twiddle_big(n2 << (L1 - RB), two_over_n, false));
+#endif
+#endif
+    AM_TL(3);
+#ifdef AM_X_NOSTORE
+    if (v[0].x != 12345.678f && v[5].y != 3.25f) return;
+#endif
+#pragma unroll
+    for (int l = 0; l < NB; ++l)
+#pragma unroll
+        for (int s = 0; s < R; ++s)
+            Ap[((size_t)(q + l * (F::GT >> LT) + s * ((1 << L1) >> RB)) << log2n2) + n2] = v[l * R + s];
+    AM_TL(4);
+}
+
 // grid (N2 / T, pairs).  A[pair][k1][n2] = W_N^{n2 k1} * sum_{n1} z[n1 N2 + n2] W_N1^{n1 k1}
 template <int L1, int LT, int E>
 __global__ void __launch_bounds__(ColCfg<L1, LT, E>::THREADS, ColCfg<L1, LT, E>::MINB_FWD)
@@ -251,11 +324,19 @@ k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__rest
     typedef ColCfg<L1, LT, E> Cfg;
     typedef RegFFT<L1, Cfg::LT, false, E> F;
     constexpr int EPT = E;
+    static_assert(EPT / (1 << F::bits_at(F::NST - 1)) <= 4, "twiddle step exponent");
     extern __shared__ float2 sm_all[];
     const int tid = threadIdx.x, pair = blockIdx.y;
     const int n2_0 = blockIdx.x << Cfg::LT;
     float2 v[EPT];
+    AM_TL(0);
     const long long v0 = g.g0 + (long long)(2 * pair) * g.VN;
+#ifdef AM_X_NOLOAD
+    if (g.VN > 0) {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) v[j] = make_float2((float)(tid + j), (float)(j * pair));
+    } else
+#endif
     if (pair_in_range(g.sv, v0, g.VN, 1ll << (L1 + log2n2), 2 * pair + 1 < g.nblocks)) {
         if (g.sv.fmt == FMT_I16_MONO) {
             const long long f0 = v0 - g.sv.lead - g.sv.buf_first + n2_0;
@@ -276,20 +357,133 @@ k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__rest
             v[j] = load_pair(g, pair, ((long long)idx << log2n2) + n2_0 + t);
         }
     }
-    F::run(v, sm_all, tid, tw);
-    const float two_over_n = 2.0f / (float)(1u << (L1 + log2n2));
-    float2 *Ap = A + ((size_t)pair << (L1 + log2n2));
-    constexpr int RB = F::bits_at(F::NST - 1), R = 1 << RB, NB = EPT / R;
+    AM_TL(1);
+    col_fwd_finish<L1, Cfg::LT, E>(v, sm_all, tid, tw, log2n2, n2_0, A + ((size_t)pair << (L1 + log2n2)));
+}
+
+// Persistent variant of k_col_fwd: grid = CTAs resident on the GPU, tiles (tile = pair * (N2 / T) + column tile) are
+// handed out dynamically.  The raw frames of the NEXT tile (2 blocks x N1 rows x T frames) are fetched by TMA
+// (cp.async.bulk.tensor.2d, boxes of T columns x 256 rows) into their own shared-memory buffer while the current
+// tile is transformed.  Why TMA: a tile is 1024 scattered
+// 32-byte pieces; as LDG / cp.async they occupy the SM's load-miss tracking (measured: 2 CTAs/SM reach 2.3 / 4.4 TB/s
+// on this pattern and the issuing warps block meanwhile, 58 % of a CTA's life in k_col_fwd), while one thread hands
+// TMA the four boxes and every warp goes on to the transform.
+// The tensor map views the PCM buffer as rows of N2 frames with a row pitch of N2 frames but 2 N2 columns (rows
+// overlap), so that a tile starting at frame f = r N2 + c (c < N2) is the box at (c, r) even when c + 16 > N2.
+// Tiles that are not fully resident take the checked scalar loads.
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned smem_dst, const void *tmap, unsigned bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+struct alignas(64) TensorMap { unsigned long long opaque[16]; };     // CUtensorMap (128 bytes), encoded by the host
+template <int FMT> struct RawFrame { typedef short type; };                       // FMT_I16_MONO
+template <> struct RawFrame<FMT_I16_STEREO> { typedef short2 type; };
+template <> struct RawFrame<FMT_F32_MONO> { typedef float type; };
+template <int FMT> __device__ __forceinline__ float frame_to_f32(typename RawFrame<FMT>::type x);
+template <> __device__ __forceinline__ float frame_to_f32<FMT_I16_MONO>(short x) { return __fmul_rn(s16_to_f32((int)x), 1.0f / 65535.0f); }
+template <> __device__ __forceinline__ float frame_to_f32<FMT_I16_STEREO>(short2 x) { return pcm_scale_sum((int)x.x + (int)x.y); }
+template <> __device__ __forceinline__ float frame_to_f32<FMT_F32_MONO>(float x) { return x; }
+
+template <int L1, int LT, int E, int FMT> struct ColStreamCfg {
+    typedef ColCfg<L1, LT, E> Cfg;
+    typedef typename RawFrame<FMT>::type Frame;
+    static constexpr int THREADS = Cfg::THREADS;
+    static constexpr int T = 1 << LT;
+    static constexpr int BOX_ROWS = (1 << L1) < 256 ? (1 << L1) : 256;
+    static constexpr size_t XCHG = Cfg::SMEM;                          // exchange buffer
+    static constexpr size_t RAW = (size_t)2 * (1 << L1) * T * sizeof(Frame);
+    static constexpr size_t SMEM = XCHG + RAW;
+    // TMA wants 16-byte box rows and a 128-byte aligned destination; two CTAs per SM must still fit
+    static constexpr bool OK = XCHG % 128 == 0 && (T * sizeof(Frame)) % 16 == 0 && SMEM <= 110 * 1024;
+};
+template <int L1, int LT, int E, int FMT>
+__global__ void __launch_bounds__(ColStreamCfg<L1, LT, E, FMT>::THREADS, ColCfg<L1, LT, E>::MINB_FWD)
+k_col_fwd_stream(const __grid_constant__ TensorMap tm, BlockGroup g, int log2n2, float2 *__restrict__ A,
+                 const float2 *__restrict__ tw, int ntiles, int *__restrict__ next_tile) {
+    typedef ColStreamCfg<L1, LT, E, FMT> SC;
+    typedef typename SC::Frame Frame;
+    typedef RegFFT<L1, LT, false, E> F;
+    constexpr int N1 = 1 << L1, T = SC::T;
+    extern __shared__ __align__(128) float2 sm_all[];
+    __shared__ __align__(8) unsigned long long bar_store;
+    __shared__ int s_next;
+    Frame *raw = (Frame *)((char *)sm_all + SC::XCHG);
+    const unsigned raw_a = (unsigned)__cvta_generic_to_shared(raw), bar = (unsigned)__cvta_generic_to_shared(&bar_store);
+    const int tid = threadIdx.x;
+    const int ltx = log2n2 - LT;                                       // log2 of column tiles per pair
+    // frame offset of the tile in the buffer, or -1 when the tile needs the checked loads (CTA-uniform)
+    auto tile_f0 = [&](int tile) -> long long {
+        const int pair = tile >> ltx, n2_0 = (tile & ((1 << ltx) - 1)) << LT;
+        const long long v0 = g.g0 + (long long)(2 * pair) * g.VN;
+        if (!pair_in_range(g.sv, v0, g.VN, 1ll << (L1 + log2n2), 2 * pair + 1 < g.nblocks)) return -1;
+        return v0 - g.sv.lead - g.sv.buf_first + n2_0;
+    };
+    auto prefetch = [&](int tile) {                                    // thread 0 only
+        const long long f0 = tile_f0(tile);
+        if (f0 < 0) return;
+        mbar_expect_tx(bar, (unsigned)SC::RAW);
 #pragma unroll
-    for (int l = 0; l < NB; ++l) {
-        const int id = tid + l * F::GT;
-        const int t = id & (Cfg::T - 1), q = id >> Cfg::LT;
-        const unsigned n2 = n2_0 + t;
-        // k1 = q + s (N1 / R): W_N^{n2 k1} = W_N^{n2 q} (W_N^{n2 N1 / R})^s
-        twiddle_geo<R>(&v[l * R], twiddle_big(n2 * (unsigned)q, two_over_n, false),
-                       twiddle_big(n2 << (L1 - RB), two_over_n, false));
+        for (int blk = 0; blk < 2; ++blk) {
+            const long long fb = f0 + blk * g.VN;
+            const int c = (int)(fb & ((1ll << log2n2) - 1)), r = (int)(fb >> log2n2);
 #pragma unroll
-        for (int s = 0; s < R; ++s) Ap[((size_t)(q + s * ((1 << L1) >> RB)) << log2n2) + n2] = v[l * R + s];
+            for (int h = 0; h < N1 / SC::BOX_ROWS; ++h)
+                tma_load_2d(raw_a + (unsigned)((blk * N1 + h * SC::BOX_ROWS) * T * sizeof(Frame)), &tm, bar, c, r + h * SC::BOX_ROWS);
+        }
+    };
+    // Tiles are handed out dynamically (*next_tile counts the tiles claimed beyond the first gridDim.x): the two CTAs of an SM do not progress at
+    // the same rate (measured 10 k vs 21 k cycles per tile), a static stride would leave the faster one idle.
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) prefetch(tile);
+    unsigned parity = 0;
+    while (tile < ntiles) {
+        const int pair = tile >> ltx, n2_0 = (tile & ((1 << ltx) - 1)) << LT;
+        float2 v[E];
+        AM_TL_SET(tile);
+        AM_TL(0);
+        int claimed = 0;
+        if (tid == 0) claimed = (int)gridDim.x + atomicAdd(next_tile, 1);    // in flight while the tile is unpacked
+        if (tile_f0(tile) >= 0) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            AM_TL(5);
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                int idx, t;
+                F::template in_coord<0>(tid, j, idx, t);
+                v[j] = make_float2(frame_to_f32<FMT>(raw[idx * T + t]), frame_to_f32<FMT>(raw[(N1 + idx) * T + t]));
+            }
+        } else {
+            AM_TL(5);
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                int idx, t;
+                F::template in_coord<0>(tid, j, idx, t);
+                v[j] = load_pair(g, pair, ((long long)idx << log2n2) + n2_0 + t);
+            }
+        }
+        if (tid == 0) s_next = claimed;
+        __syncthreads();                       // raw tile consumed by everyone; previous tile's exchange reads done
+        const int next = s_next;
+        if (tid == 0 && next < ntiles) prefetch(next);
+        AM_TL(1);
+        col_fwd_finish<L1, LT, E>(v, sm_all, tid, tw, log2n2, n2_0, A + ((size_t)pair << (L1 + log2n2)));
+        tile = next;
     }
 }
 
@@ -499,7 +693,15 @@ k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restr
             F::template in_coord<0>(gtid, j, idx, t);
             v[j] = Ar[idx];
         }
+        AM_TL(0);
+        AM_TL_WAIT(v, 32);
+        AM_TL(1);
+#ifdef AM_X_SWAP
+        I::run(v, sm, gtid, tw);
+#else
         F::run(v, sm, gtid, tw);
+#endif
+        AM_TL(2);
         if constexpr (MODE == ROW_FORWARD) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -518,14 +720,106 @@ k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restr
         if constexpr (MODE == ROW_INVERSE) v[j] = Ar[idx];
         v[j] = amfft::cmul(v[j], __ldg(&Sr[idx]));
     }
+    AM_TL_WAIT(v, 32);
+    AM_TL(3);
     if constexpr (MODE == ROW_FUSED) __syncthreads();
+#ifdef AM_X_SWAP
+    F::run(v, sm, gtid, tw);
+#else
     I::run(v, sm, gtid, tw);
+#endif
+    AM_TL(4);
     float2 *Or = (MODE == ROW_INVERSE) ? Bout + ((size_t)row << L2) : Ar;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         int idx, t;
         I::out_coord(gtid, j, idx, t);
         Or[idx] = v[j];
+    }
+    AM_TL(5);
+}
+
+// Persistent variant of k_row32<L2, ROW_FUSED>: grid = resident CTAs, rows handed out dynamically.  The row kernel
+// spends ~40 % of a CTA's life waiting (launch + row load, spectrum load, store drain; timeline in DESIGN.md) and two
+// CTAs of 8 warps cannot fill the issue slots while one of them waits.  Here the exchange buffer doubles as the
+// landing zone of bulk asynchronous copies (cp.async.bulk, 64 KB each) issued by one thread at the two points where
+// the buffer is idle: the snippet-spectrum row arrives during the last forward butterflies, the NEXT row of A during
+// the last inverse butterflies and the stores, so both loads are off the critical path and cost no registers.
+__device__ __forceinline__ void bulk_load(unsigned smem_dst, const void *gsrc, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+template <int L2>
+__global__ void __launch_bounds__(Row32Cfg<L2>::THREADS, 2)
+k_row32_stream(float2 *__restrict__ A, const float2 *__restrict__ spec, int log2n1, int rows,
+               const float2 *__restrict__ tw, int *__restrict__ next_row) {
+    typedef RegFFT<L2, 0, false, 32> F;
+    typedef RegFFT<L2, 0, true, 32> I;
+    constexpr unsigned ROW_BYTES = (unsigned)sizeof(float2) << L2, PIECE = 16384;
+    extern __shared__ __align__(128) float2 sm[];
+    __shared__ __align__(8) unsigned long long bar_store[2];
+    __shared__ int s_next;
+    const int gtid = threadIdx.x;
+    const unsigned sm_a = (unsigned)__cvta_generic_to_shared(sm);
+    const unsigned bar_row = (unsigned)__cvta_generic_to_shared(&bar_store[0]);
+    const unsigned bar_spec = (unsigned)__cvta_generic_to_shared(&bar_store[1]);
+    auto fetch = [&](const float2 *src, unsigned bar) {                 // one thread; the buffer must be idle
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, ROW_BYTES);
+#pragma unroll
+        for (unsigned o = 0; o < ROW_BYTES; o += PIECE) bulk_load(sm_a + o, (const char *)src + o, PIECE, bar);
+    };
+    if (gtid == 0) {
+        mbar_init(bar_row, 1);
+        mbar_init(bar_spec, 1);
+    }
+    __syncthreads();
+    int row = blockIdx.x;
+    if (gtid == 0 && row < rows) fetch(A + ((size_t)row << L2), bar_row);
+    unsigned parity = 0;
+    while (row < rows) {
+        float2 *Ar = A + ((size_t)row << L2);
+        int claimed = 0;
+        if (gtid == 0) claimed = (int)gridDim.x + atomicAdd(next_row, 1);
+        float2 v[32];
+        AM_TL_SET(row);
+        AM_TL(0);
+        mbar_wait(bar_row, parity);
+        AM_TL(1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int idx, t;
+            F::template in_coord<0>(gtid, j, idx, t);
+            v[j] = sm[idx];
+        }
+        if (gtid == 0) s_next = claimed;
+        __syncthreads();                                               // row copied out; the buffer becomes the exchange buffer
+        AM_TL(2);
+        const float2 *Sr = spec + ((size_t)(row & ((1 << log2n1) - 1)) << L2);
+        F::run_hook(v, sm, gtid, tw, [&] { if (gtid == 0) fetch(Sr, bar_spec); });
+        AM_TL(3);
+        mbar_wait(bar_spec, parity);
+        AM_TL(4);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int idx, t;
+            I::template in_coord<0>(gtid, j, idx, t);                  // == F::out_coord: no exchange across the multiply
+            v[j] = amfft::cmul(v[j], sm[idx]);
+        }
+        __syncthreads();
+        AM_TL(5);
+        const int next = s_next;
+        I::run_hook(v, sm, gtid, tw, [&] { if (gtid == 0 && next < rows) fetch(A + ((size_t)next << L2), bar_row); });
+        AM_TL(6);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            int idx, t;
+            I::out_coord(gtid, j, idx, t);
+            Ar[idx] = v[j];
+        }
+        AM_TL(7);
+        parity ^= 1;
+        row = next;
     }
 }
 

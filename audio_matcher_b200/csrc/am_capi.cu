@@ -217,8 +217,10 @@ bool encode_pcm_tensor_map(amk::TensorMap *out, const amk::StreamView &sv, int l
 // true = launched; false with last_status() == AM_OK = not applicable (the caller falls back to k_col_fwd)
 thread_local am_status tl_status = AM_OK;
 am_status last_status() { return tl_status; }
-template <int L1, int LT, int E, int FMT>
+template <int L1, int LT, int E, int FMT, int L2C = -1>
 bool launch_col_stream(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *A, dim3 grid) {
+    if constexpr (L2C < 0 && L1 == 9 && LT == 4 && E == 32 && FMT == amk::FMT_I16_MONO)
+        if (l2 == 13) return launch_col_stream<L1, LT, E, FMT, 13>(h, g, l2, A, grid);
     typedef amk::ColStreamCfg<L1, LT, E, FMT> SC;
     tl_status = AM_OK;
     if constexpr (!SC::OK) return false;
@@ -231,16 +233,16 @@ bool launch_col_stream(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *
             int dev = 0, sms = 0, per_sm = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaFuncSetAttribute(amk::k_col_fwd_stream<L1, LT, E, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC::SMEM);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amk::k_col_fwd_stream<L1, LT, E, FMT>, SC::THREADS, SC::SMEM);
+            cudaFuncSetAttribute(amk::k_col_fwd_stream<L1, LT, E, FMT, L2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC::SMEM);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amk::k_col_fwd_stream<L1, LT, E, FMT, L2C>, SC::THREADS, SC::SMEM);
             return sms * (per_sm > 0 ? per_sm : 1);
         }();
         const int ntiles = (int)(grid.x * grid.y), nctas = ntiles < ctas ? ntiles : ctas;
         auto body = [&]() -> am_status {
-            TRY(set_smem(amk::k_col_fwd_stream<L1, LT, E, FMT>, SC::SMEM));
+            TRY(set_smem(amk::k_col_fwd_stream<L1, LT, E, FMT, L2C>, SC::SMEM));
             TRY(h->d_sched.reserve(1));
             CU(cudaMemsetAsync(h->d_sched.p, 0, sizeof(int), h->stream));
-            LAUNCH(h, AM_K_COL_FWD, amk::k_col_fwd_stream<L1, LT, E, FMT><<<nctas, SC::THREADS, SC::SMEM, h->stream>>>(tm, g, l2, A, h->d_tw.p, ntiles, h->d_sched.p));
+            LAUNCH(h, AM_K_COL_FWD, amk::k_col_fwd_stream<L1, LT, E, FMT, L2C><<<nctas, SC::THREADS, SC::SMEM, h->stream>>>(tm, g, l2, A, h->d_tw.p, ntiles, h->d_sched.p));
             return AM_OK;
         };
         tl_status = body();
@@ -253,6 +255,13 @@ template <int L1, int LT, int E, bool INV> am_status launch_col_t(am_matcher *h,
     int pairs = (g.nblocks + 1) / 2;
     dim3 grid((1u << l2) >> Cfg::LT, pairs);
     if (INV) {
+        if constexpr (L1 == 9 && LT == 4 && E == 32) {
+            if (l2 == 13) {                   // the N = 2^22 shape (cfg 2 / 3): column pitch known at compile time
+                TRY(set_smem(amk::k_col_inv<L1, LT, E, 13>, Cfg::SMEM_INV));
+                LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT, E, 13><<<grid, Cfg::THREADS, Cfg::SMEM_INV, h->stream>>>(g, l2, A, h->d_tw.p));
+                return AM_OK;
+            }
+        }
         TRY(set_smem(amk::k_col_inv<L1, LT, E>, Cfg::SMEM_INV));
         LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT, E><<<grid, Cfg::THREADS, Cfg::SMEM_INV, h->stream>>>(g, l2, A, h->d_tw.p));
     } else {
@@ -292,8 +301,12 @@ template <bool INV> am_status launch_col(am_matcher *h, int l1, const amk::Block
         if (ept == 32) return launch_col_t<9, 4, 32, INV>(h, g, l2, A);
         if (lt_env == 3) return launch_col_t<9, 3, 16, INV>(h, g, l2, A);
         return launch_col_t<9, 4, 16, INV>(h, g, l2, A);
-    case 10:                                  // 1024-point columns: 16 elements per thread measured faster both ways
-        if (ept == 32 && getenv("AM_COL10_EPT32")) return launch_col_t<10, 4, 32, INV>(h, g, l2, A);
+    case 10:                                  // 1024-point columns: inverse tiles are faster with 16 elements per thread
+        if (!INV && !ept_fwd_set) return launch_col_t<10, 3, 32, INV>(h, g, l2, A);     // TMA-fed forward: 8.3 vs 11.4 ms (cfg 4, 30 h)
+        if (ept == 32 && getenv("AM_COL10_EPT32")) {
+            if (atoi(getenv("AM_COL10_EPT32")) == 3) return launch_col_t<10, 3, 32, INV>(h, g, l2, A);
+            return launch_col_t<10, 4, 32, INV>(h, g, l2, A);
+        }
         if (lt_env == 4) return launch_col_t<10, 4, 16, INV>(h, g, l2, A);
         return launch_col_t<10, 3, 16, INV>(h, g, l2, A);
     }
@@ -320,8 +333,9 @@ am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, 
         if (ept == 32) {
             typedef amk::Row32Cfg<L2> C32;
             if constexpr (MODE == amk::ROW_FUSED) {
-                // persistent kernel fed by bulk asynchronous copies (AM_ROW_STREAM=0: off)
-                static const bool stream_on = [] { const char *v = getenv("AM_ROW_STREAM"); return !(v && *v == '0'); }();
+                // persistent kernel fed by bulk asynchronous copies: hides the load waits but measured no faster
+                // (12.0 vs 11.6 ms per 24 h; the transforms themselves bound the row pass) -- opt-in, AM_ROW_STREAM=1
+                static const bool stream_on = [] { const char *v = getenv("AM_ROW_STREAM"); return v && *v == '1'; }();
                 if (stream_on) {
                     static const int ctas = [] {
                         const char *v = getenv("AM_ROW_STREAM_CTAS");

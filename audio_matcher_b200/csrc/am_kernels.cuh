@@ -87,13 +87,15 @@ struct BlockGroup {
     float theta;
 };
 
+template <bool SCALE = true>
 __device__ __forceinline__ void store_pair(const BlockGroup &g, int pair, long long n, float2 val) {
     if (n >= g.VN) return;
+    const float sc = SCALE ? g.scalar : 1.0f;
     long long o = g.g0 + (long long)(2 * pair) * g.VN + n;
-    if (o < g.g_end) g.c[o - g.c_g0] = val.x * g.scalar;
+    if (o < g.g_end) g.c[o - g.c_g0] = val.x * sc;
     if (2 * pair + 1 < g.nblocks) {
         o += g.VN;
-        if (o < g.g_end) g.c[o - g.c_g0] = val.y * g.scalar;
+        if (o < g.g_end) g.c[o - g.c_g0] = val.y * sc;
     }
 }
 __device__ __forceinline__ float2 load_pair(const BlockGroup &g, int pair, long long n) {
@@ -409,10 +411,11 @@ template <int L1, int LT, int E, int FMT> struct ColStreamCfg {
     // TMA wants 16-byte box rows and a 128-byte aligned destination; two CTAs per SM must still fit
     static constexpr bool OK = XCHG % 128 == 0 && (T * sizeof(Frame)) % 16 == 0 && SMEM <= 110 * 1024;
 };
-template <int L1, int LT, int E, int FMT>
+template <int L1, int LT, int E, int FMT, int L2C = -1>
 __global__ void __launch_bounds__(ColStreamCfg<L1, LT, E, FMT>::THREADS, ColCfg<L1, LT, E>::MINB_FWD)
-k_col_fwd_stream(const __grid_constant__ TensorMap tm, BlockGroup g, int log2n2, float2 *__restrict__ A,
+k_col_fwd_stream(const __grid_constant__ TensorMap tm, BlockGroup g, int log2n2_arg, float2 *__restrict__ A,
                  const float2 *__restrict__ tw, int ntiles, int *__restrict__ next_tile) {
+    const int log2n2 = L2C >= 0 ? L2C : log2n2_arg;
     typedef ColStreamCfg<L1, LT, E, FMT> SC;
     typedef typename SC::Frame Frame;
     typedef RegFFT<L1, LT, false, E> F;
@@ -488,12 +491,14 @@ k_col_fwd_stream(const __grid_constant__ TensorMap tm, BlockGroup g, int log2n2,
 }
 
 // grid (N2 / T, pairs).  y[n1 N2 + n2] = sum_{k1} W_N1^{-n1 k1} W_N^{-n2 k1} B[k1][n2]
-template <int L1, int LT, int E>
+// L2C >= 0: log2 N2 known at compile time (the hot shapes; folds the tile addressing into immediates)
+template <int L1, int LT, int E, int L2C = -1>
 __global__ void __launch_bounds__(ColCfg<L1, LT, E>::THREADS, ColCfg<L1, LT, E>::MINB_INV)
-k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *__restrict__ tw) {
+k_col_inv(BlockGroup g, int log2n2_arg, const float2 *__restrict__ A, const float2 *__restrict__ tw) {
     typedef ColCfg<L1, LT, E> Cfg;
     typedef RegFFT<L1, Cfg::LT, true, E> I;
     constexpr int EPT = E;
+    const int log2n2 = L2C >= 0 ? L2C : log2n2_arg;
     extern __shared__ float2 sm_all[];
     const int tid = threadIdx.x, pair = blockIdx.y;
     const int n2_0 = blockIdx.x << Cfg::LT;
@@ -508,8 +513,10 @@ k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *
         const unsigned n2 = n2_0 + t;
 #pragma unroll
         for (int r = 0; r < R; ++r) v[l * R + r] = Ap[((size_t)(q + r * ((1 << L1) >> RB)) << log2n2) + n2];
-        twiddle_geo<R>(&v[l * R], twiddle_big(n2 * (unsigned)q, two_over_n, true),
-                       twiddle_big(n2 << (L1 - RB), two_over_n, true));
+        float2 base = twiddle_big(n2 * (unsigned)q, two_over_n, true);
+        base.x *= g.scalar;                                         // the output scale rides on the twiddles
+        base.y *= g.scalar;
+        twiddle_geo<R>(&v[l * R], base, twiddle_big(n2 << (L1 - RB), two_over_n, true));
     }
     I::run(v, sm_all, tid, tw);
     const long long o0 = g.g0 + (long long)(2 * pair) * g.VN;
@@ -526,7 +533,7 @@ k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *
             for (int j = 0; j < EPT; ++j) {
                 int n1, t;
                 I::out_coord(tid, j, n1, t);
-                sm_all[n1 * 16 + ((((t >> 1) ^ (n1 & 7)) << 1) | (t & 1))] = make_float2(v[j].x * g.scalar, v[j].y * g.scalar);
+                sm_all[n1 * 16 + ((((t >> 1) ^ (n1 & 7)) << 1) | (t & 1))] = v[j];
             }
             __syncthreads();
             for (int row = tid; row < (1 << L1); row += Cfg::THREADS) {
@@ -548,9 +555,15 @@ k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *
                     if (left <= 0) continue;
                     const int valid = left < 16 ? (int)left : 16;
                     float mn = vals[0], mx = vals[0], last = vals[0];
+                    if (valid == 16) {
 #pragma unroll
-                    for (int i = 1; i < 16; ++i)
-                        if (i < valid) { mn = fminf(mn, vals[i]); mx = fmaxf(mx, vals[i]); last = vals[i]; }
+                        for (int i = 1; i < 16; ++i) { mn = fminf(mn, vals[i]); mx = fmaxf(mx, vals[i]); }
+                        last = vals[15];
+                    } else {
+#pragma unroll
+                        for (int i = 1; i < 16; ++i)
+                            if (i < valid) { mn = fminf(mn, vals[i]); mx = fmaxf(mx, vals[i]); last = vals[i]; }
+                    }
                     const long long ci = o - g.c_g0;
                     g.rsum[ci >> 4] = make_float4(mn, mx, vals[0], last);
                     if (mx >= g.theta) {
@@ -580,8 +593,8 @@ k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *
             I::out_coord(tid, j, n1, t);
             const int n = (n1 << log2n2) + n2_0 + t;
             if (n < vn) {
-                c0[n] = v[j].x * g.scalar;
-                c0[n + vn] = v[j].y * g.scalar;
+                c0[n] = v[j].x;
+                c0[n + vn] = v[j].y;
             }
         }
     } else {
@@ -589,7 +602,7 @@ k_col_inv(BlockGroup g, int log2n2, const float2 *__restrict__ A, const float2 *
         for (int j = 0; j < EPT; ++j) {
             int n1, t;
             I::out_coord(tid, j, n1, t);
-            store_pair(g, pair, ((long long)n1 << log2n2) + n2_0 + t, v[j]);
+            store_pair<false>(g, pair, ((long long)n1 << log2n2) + n2_0 + t, v[j]);
         }
     }
 }

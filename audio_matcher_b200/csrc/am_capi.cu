@@ -219,7 +219,9 @@ thread_local am_status tl_status = AM_OK;
 am_status last_status() { return tl_status; }
 template <int L1, int LT, int E, int FMT, int L2C = -1>
 bool launch_col_stream(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *A, dim3 grid) {
-    if constexpr (L2C < 0 && L1 == 9 && LT == 4 && E == 32 && FMT == amk::FMT_I16_MONO)
+    if constexpr (L2C < 0 && ((L1 == 9 && LT == 4 && E == 32 && FMT == amk::FMT_I16_MONO) ||
+                              (L1 == 10 && LT == 3 && E == 32 && FMT == amk::FMT_I16_MONO) ||
+                              (L1 == 7 && LT == 4 && E == 16 && FMT == amk::FMT_I16_STEREO)))
         if (l2 == 13) return launch_col_stream<L1, LT, E, FMT, 13>(h, g, l2, A, grid);
     typedef amk::ColStreamCfg<L1, LT, E, FMT> SC;
     tl_status = AM_OK;
@@ -255,8 +257,8 @@ template <int L1, int LT, int E, bool INV> am_status launch_col_t(am_matcher *h,
     int pairs = (g.nblocks + 1) / 2;
     dim3 grid((1u << l2) >> Cfg::LT, pairs);
     if (INV) {
-        if constexpr (L1 == 9 && LT == 4 && E == 32) {
-            if (l2 == 13) {                   // the N = 2^22 shape (cfg 2 / 3): column pitch known at compile time
+        if constexpr ((L1 == 9 && LT == 4 && E == 32) || (L1 == 10 && LT == 3 && E == 16) || (L1 == 7 && LT == 4 && E == 16)) {
+            if (l2 == 13) {                   // N = 2^22 / 2^23 / 2^20 with 8192-point rows: column pitch known at compile time
                 TRY(set_smem(amk::k_col_inv<L1, LT, E, 13>, Cfg::SMEM_INV));
                 LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT, E, 13><<<grid, Cfg::THREADS, Cfg::SMEM_INV, h->stream>>>(g, l2, A, h->d_tw.p));
                 return AM_OK;

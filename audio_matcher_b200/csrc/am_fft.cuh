@@ -275,18 +275,23 @@ template <int LOG2N, int LOG2B, bool INV, int E = EPT> struct RegFFT {
 #ifdef __CUDACC__
     // Full transform on the device.  On entry v holds the stage-0 inputs (see in_coord<0>),
     // on exit the natural-order outputs (see out_coord).  All threads of the CTA must call.
-    template <int ST = 0> static __device__ __forceinline__ void run(float2 (&v)[EPT], float2 *sm, int gtid,
-                                                                     const float2 *__restrict__ tw) {
+    // TAIL_SYNC = false leaves out the barrier after the last exchange read: the caller then guarantees a
+    // __syncthreads() before the buffer is written again.
+    // LEAD_SYNC = true puts a barrier in front of the first exchange write (after the first butterflies) for a
+    // caller whose threads may still be reading the buffer when they enter.
+    template <int ST = 0, bool TAIL_SYNC = true, bool LEAD_SYNC = false>
+    static __device__ __forceinline__ void run(float2 (&v)[EPT], float2 *sm, int gtid, const float2 *__restrict__ tw) {
         butterfly<ST>(v, gtid, tw);
         AM_TL(8 + (INV ? 9 : 0) + ST * 3);
         if constexpr (ST + 1 < NST) {
+            if constexpr (ST == 0 && LEAD_SYNC) __syncthreads();
             xchg_write<ST>(v, sm, gtid);
             __syncthreads();
             AM_TL(8 + (INV ? 9 : 0) + ST * 3 + 1);
             xchg_read<ST + 1>(v, sm, gtid);
-            __syncthreads();
+            if constexpr (TAIL_SYNC || ST + 2 < NST) __syncthreads();
             AM_TL(8 + (INV ? 9 : 0) + ST * 3 + 2);
-            run<ST + 1>(v, sm, gtid, tw);
+            run<ST + 1, TAIL_SYNC, LEAD_SYNC>(v, sm, gtid, tw);
         }
     }
     // Same, calling hook() once when the exchange buffer has been read for the last time (before the last stage's

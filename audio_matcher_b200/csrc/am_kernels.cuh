@@ -20,6 +20,10 @@
 #pragma once
 #include "am_fft.cuh"
 
+#ifndef AM_X_ROWSYNC
+#define AM_X_ROWSYNC 0
+#endif
+
 namespace amk {
 
 using amfft::EPT;
@@ -283,12 +287,12 @@ template <int R, int NB> __device__ __forceinline__ void twiddle_geo_all(float2 
 }
 
 // column transform of one tile held in registers, four-step twiddle, store to A[pair][k1][n2]
-template <int L1, int LT, int E>
+template <int L1, int LT, int E, bool TAIL_SYNC = true>
 __device__ __forceinline__ void col_fwd_finish(float2 (&v)[E], float2 *sm_all, int tid, const float2 *__restrict__ tw,
                                                int log2n2, int n2_0, float2 *__restrict__ Ap) {
     typedef RegFFT<L1, LT, false, E> F;
 #ifndef AM_X_NOFFT
-    F::run(v, sm_all, tid, tw);
+    F::template run<0, TAIL_SYNC>(v, sm_all, tid, tw);
 #endif
     AM_TL(2);
     const float two_over_n = 2.0f / (float)(1u << (L1 + log2n2));
@@ -485,7 +489,8 @@ k_col_fwd_stream(const __grid_constant__ TensorMap tm, BlockGroup g, int log2n2_
         const int next = s_next;
         if (tid == 0 && next < ntiles) prefetch(next);
         AM_TL(1);
-        col_fwd_finish<L1, LT, E>(v, sm_all, tid, tw, log2n2, n2_0, A + ((size_t)pair << (L1 + log2n2)));
+        // (the barrier above separates this tile's exchange writes from the previous tile's last exchange reads)
+        col_fwd_finish<L1, LT, E, false>(v, sm_all, tid, tw, log2n2, n2_0, A + ((size_t)pair << (L1 + log2n2)));
         tile = next;
     }
 }
@@ -712,7 +717,12 @@ k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restr
 #ifdef AM_X_SWAP
         I::run(v, sm, gtid, tw);
 #else
+#if AM_X_ROWSYNC == 0
+        if constexpr (MODE == ROW_FUSED) F::template run<0, false>(v, sm, gtid, tw);   // the inverse's lead barrier covers it
+        else F::run(v, sm, gtid, tw);
+#else
         F::run(v, sm, gtid, tw);
+#endif
 #endif
         AM_TL(2);
         if constexpr (MODE == ROW_FORWARD) {
@@ -735,11 +745,19 @@ k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restr
     }
     AM_TL_WAIT(v, 32);
     AM_TL(3);
-    if constexpr (MODE == ROW_FUSED) __syncthreads();
 #ifdef AM_X_SWAP
     F::run(v, sm, gtid, tw);
 #else
+    // fused: the forward transform's last exchange reads must be over before the inverse writes (barrier after the
+    // first inverse butterflies); nothing touches the buffer after the inverse
+#if AM_X_ROWSYNC == 0
+    I::template run<0, false, MODE == ROW_FUSED>(v, sm, gtid, tw);
+#elif AM_X_ROWSYNC == 1
+    if constexpr (MODE == ROW_FUSED) __syncthreads();
     I::run(v, sm, gtid, tw);
+#else
+    I::template run<0, false, false>(v, sm, gtid, tw);
+#endif
 #endif
     AM_TL(4);
     float2 *Or = (MODE == ROW_INVERSE) ? Bout + ((size_t)row << L2) : Ar;

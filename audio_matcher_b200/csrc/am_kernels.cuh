@@ -432,18 +432,25 @@ k_col_fwd_stream(const __grid_constant__ TensorMap tm, BlockGroup g, int log2n2_
     const int tid = threadIdx.x;
     const int ltx = log2n2 - LT;                                       // log2 of column tiles per pair
     // frame offset of the tile in the buffer, or -1 when the tile needs the checked loads (CTA-uniform)
+    // (a last pair that holds a single block is fetched as one block; its imaginary half is zero)
     auto tile_f0 = [&](int tile) -> long long {
         const int pair = tile >> ltx, n2_0 = (tile & ((1 << ltx) - 1)) << LT;
         const long long v0 = g.g0 + (long long)(2 * pair) * g.VN;
-        if (!pair_in_range(g.sv, v0, g.VN, 1ll << (L1 + log2n2), 2 * pair + 1 < g.nblocks)) return -1;
-        return v0 - g.sv.lead - g.sv.buf_first + n2_0;
+        const bool two = 2 * pair + 1 < g.nblocks;
+        const long long lo = v0 - g.sv.lead, hi = lo + (two ? g.VN : 0) + (1ll << (L1 + log2n2));
+        long long lim = g.sv.buf_first + g.sv.buf_frames;
+        if (lim > g.sv.total) lim = g.sv.total;
+        if (lo < g.sv.buf_first || hi > lim) return -1;
+        return lo - g.sv.buf_first + n2_0;
     };
     auto prefetch = [&](int tile) {                                    // thread 0 only
         const long long f0 = tile_f0(tile);
         if (f0 < 0) return;
-        mbar_expect_tx(bar, (unsigned)SC::RAW);
+        const int nblk = 2 * (tile >> ltx) + 1 < g.nblocks ? 2 : 1;
+        mbar_expect_tx(bar, (unsigned)(SC::RAW / 2) * nblk);
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
+            if (blk == nblk) break;
             const long long fb = f0 + blk * g.VN;
             const int c = (int)(fb & ((1ll << log2n2) - 1)), r = (int)(fb >> log2n2);
 #pragma unroll
@@ -474,6 +481,10 @@ k_col_fwd_stream(const __grid_constant__ TensorMap tm, BlockGroup g, int log2n2_
                 int idx, t;
                 F::template in_coord<0>(tid, j, idx, t);
                 v[j] = make_float2(frame_to_f32<FMT>(raw[idx * T + t]), frame_to_f32<FMT>(raw[(N1 + idx) * T + t]));
+            }
+            if (2 * pair + 1 >= g.nblocks) {                       // single block: the second half of the buffer is stale
+#pragma unroll
+                for (int j = 0; j < E; ++j) v[j].y = 0.f;
             }
         } else {
             AM_TL(5);

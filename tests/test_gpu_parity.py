@@ -459,7 +459,11 @@ def test_host_memory_path_equals_device_path(am, orc, full_size):
     a = am.calc_chunks(fs["sr"], host, fs["algo"], True, fs["conf"])
     st = fs["algo"].stats()
     b = am.calc_chunks(fs["sr"], fs["pcm"][:frames], fs["algo"], True, fs["conf"])
-    assert [(p.position.start, p.height, p.prominence) for p in a] == [(p.position.start, p.height, p.prominence) for p in b]
+    # same offsets; heights to rounding only: host streams are cut into smaller segments (the unit of the double-buffered
+    # upload), so the FFT blocks sit at other positions than on the resident path
+    assert [p.position.start for p in a] == [p.position.start for p in b]
+    for x, y in zip(a, b):
+        assert abs(x.height - y.height) <= 1e-5 * abs(y.height) and abs(x.prominence - y.prominence) <= 1e-5 * abs(y.prominence)
     assert st["h2d_bytes"] >= frames * 2 and len(a) > 0
 
 

@@ -36,9 +36,9 @@ METRIC = "audio-hours matched/sec (snippet vs stream)"
 UNIT = "audio-hours/s"
 CHUNK_S, DIST_S, PROM = 60.0, 480.0, 0.13
 # dram__bytes_read.sum + dram__bytes_write.sum per block pair at N = 2^22, from the ncu --set full capture
-# summarised in profiles/r01_ncu_full_final.csv (32-pair launches: k_row32 1.574 + 1.028 GB, k_col_fwd 0.482 + 1.021 GB,
-# k_col_inv 1.074 + 0.222 GB in summary mode)
-NCU_DRAM_BYTES_PER_PAIR_2P22 = {"k_row": 81.3e6, "k_col_fwd": 47.0e6, "k_col_inv": 40.5e6}
+# summarised in profiles/r01_ncu_full_streaming.csv (64-pair launches: k_row32 3.133 + 2.105 GB, k_col_fwd_stream
+# 0.959 + 2.092 GB, k_col_inv 2.148 + 0.459 GB in summary mode)
+NCU_DRAM_BYTES_PER_PAIR_2P22 = {"k_row": 81.8e6, "k_col_fwd": 47.7e6, "k_col_inv": 40.7e6}
 PLANT_PERIOD_S, PLANT_JITTER_S = 600.0, 30.0
 
 
@@ -290,7 +290,7 @@ def _main(out_stream):
             traffic = NCU_DRAM_BYTES_PER_PAIR_2P22[dom] * pairs / (ktimes[dom]["launches"] / args.steps)   # per launch
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                     "frac": achieved / peak_gbs, "traffic": traffic,
-                    "traffic_source": "ncu dram bytes per block pair (profiles/r01_ncu_full_final.csv) x pairs per launch",
+                    "traffic_source": "ncu dram bytes per block pair (profiles/r01_ncu_full_streaming.csv) x pairs per launch",
                     "algorithmic_bytes_per_launch": model_bytes[dom] / (ktimes[dom]["launches"] / args.steps),
                     "peak_source": peak_src,
                     "launches_per_step": ktimes[dom]["launches"] / args.steps, "ms_per_step": per_step_ms,

@@ -331,10 +331,10 @@ template <int L2, int MODE>
 am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, int l1, int rows) {
     typedef amk::RowCfg<L2> Cfg;
     static const int ept = [] { const char *v = getenv("AM_ROW_EPT"); return v && *v ? atoi(v) : 32; }();
-    if constexpr (L2 == 13) {
+    if constexpr (L2 == 13 || L2 == 12) {
         if (ept == 32) {
             typedef amk::Row32Cfg<L2> C32;
-            if constexpr (MODE == amk::ROW_FUSED) {
+            if constexpr (MODE == amk::ROW_FUSED && L2 == 13) {
                 // persistent kernel fed by bulk asynchronous copies: hides the load waits but measured no faster
                 // (12.0 vs 11.6 ms per 24 h; the transforms themselves bound the row pass) -- opt-in, AM_ROW_STREAM=1
                 static const bool stream_on = [] { const char *v = getenv("AM_ROW_STREAM"); return v && *v == '1'; }();

@@ -131,9 +131,10 @@ int main() {
     worst = std::max(worst, check_roundtrip<9>());
     worst = std::max(worst, check_roundtrip<13>());
 #define CHK32(n) worst = std::max(worst, check<n, 0, false, 32>()); worst = std::max(worst, check<n, 0, true, 32>());
-    CHK32(5) CHK32(9) CHK32(10) CHK32(13) CHK32(14)
+    CHK32(5) CHK32(9) CHK32(10) CHK32(12) CHK32(13) CHK32(14)
     worst = std::max(worst, check<9, 4, false, 32>()); worst = std::max(worst, check<9, 4, true, 32>());
     worst = std::max(worst, check<10, 4, false, 32>()); worst = std::max(worst, check<10, 4, true, 32>());
+    worst = std::max(worst, check_roundtrip<12, 32>());
     worst = std::max(worst, check_roundtrip<13, 32>());
     worst = std::max(worst, check_roundtrip<14, 32>());
     printf(worst < 2e-6 ? "ALL OK\n" : "SOME FAILED\n");

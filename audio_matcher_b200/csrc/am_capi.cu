@@ -334,10 +334,13 @@ am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, 
     if constexpr (L2 == 13 || L2 == 12) {
         if (ept == 32) {
             typedef amk::Row32Cfg<L2> C32;
-            if constexpr (MODE == amk::ROW_FUSED && L2 == 13) {
-                // persistent kernel fed by bulk asynchronous copies: hides the load waits but measured no faster
-                // (12.0 vs 11.6 ms per 24 h; the transforms themselves bound the row pass) -- opt-in, AM_ROW_STREAM=1
-                static const bool stream_on = [] { const char *v = getenv("AM_ROW_STREAM"); return v && *v == '1'; }();
+            if constexpr ((MODE == amk::ROW_FUSED || MODE == amk::ROW_INVERSE) && L2 == 13) {
+                // persistent kernel fed by bulk asynchronous copies.  Fused: hides the load waits but measured no
+                // faster (12.0 vs 11.6 ms per 24 h; the transforms themselves bound the row pass) -- opt-in,
+                // AM_ROW_STREAM=1.  Inverse-only (batch mode): the plain kernel is load-latency bound -- default,
+                // AM_ROW_STREAM=0 turns it off.
+                static const int stream_env = [] { const char *v = getenv("AM_ROW_STREAM"); return v && *v ? atoi(v) : -1; }();
+                const bool stream_on = MODE == amk::ROW_FUSED ? stream_env == 1 : stream_env != 0;
                 if (stream_on) {
                     static const int ctas = [] {
                         const char *v = getenv("AM_ROW_STREAM_CTAS");
@@ -347,10 +350,10 @@ am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, 
                         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
                         return sms * 2;
                     }();
-                    TRY(set_smem(amk::k_row32_stream<L2>, C32::SMEM));
+                    TRY(set_smem(amk::k_row32_stream<L2, MODE>, C32::SMEM));
                     TRY(h->d_sched.reserve(1));
                     CU(cudaMemsetAsync(h->d_sched.p, 0, sizeof(int), h->stream));
-                    LAUNCH(h, AM_K_ROW, amk::k_row32_stream<L2><<<rows < ctas ? rows : ctas, C32::THREADS, C32::SMEM, h->stream>>>(A, spec, l1, rows, h->d_tw.p, h->d_sched.p));
+                    LAUNCH(h, AM_K_ROW, amk::k_row32_stream<L2, MODE><<<rows < ctas ? rows : ctas, C32::THREADS, C32::SMEM, h->stream>>>(A, spec, B, l1, rows, h->d_tw.p, h->d_sched.p));
                     return AM_OK;
                 }
             }
@@ -908,7 +911,15 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     // Resident streams take 4 GB segments (~370 chunks: the per-chunk peak kernel fills the GPU, fewer ragged launch
     // groups; 25.7 -> 24.5 ms per 24 h).  Host streams keep 512 MB segments: a segment is also the unit of the
     // double-buffered upload and the first one is not overlapped with compute.
-    size_t seg_floats = (env_mb("AM_SEGMENT_MB", mem == AM_MEM_HOST ? 512 : 4096) << 20) / sizeof(float) / S;
+    size_t seg_mb = mem == AM_MEM_HOST ? 512 : 4096;
+    if (S > 1 && !getenv("AM_SEGMENT_MB")) {
+        // a batch shares the budget between its S correlation buffers; short segments mean short launch groups
+        // (measured 17.2 vs 13.5 us per snippet and block pair in the inverse row pass), so take up to a quarter of
+        // the free device memory, at most 32 GB
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) seg_mb = std::max<size_t>(seg_mb, std::min<size_t>(free_b >> 22, 32768));
+    }
+    size_t seg_floats = (env_mb("AM_SEGMENT_MB", seg_mb) << 20) / sizeof(float) / S;
     if (S > 1) seg_floats = std::max<size_t>(seg_floats, (size_t)48 << 20);
     long long K = std::max<long long>(1, (long long)(seg_floats / (size_t)C));
     K = std::min<long long>(K, (long long)num_chunks);

@@ -23,6 +23,9 @@
 #ifndef AM_X_ROWSYNC
 #define AM_X_ROWSYNC 0
 #endif
+#ifndef AM_X_ROWORDER
+#define AM_X_ROWORDER 1
+#endif
 
 namespace amk {
 
@@ -713,7 +716,10 @@ k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restr
     typedef RegFFT<L2, 0, true, 32> I;
     extern __shared__ float2 sm[];
     const int gtid = threadIdx.x;
-    const int row = blockIdx.x;
+    // k1-major order: consecutive CTAs take row k1 of every block pair of the group, so a spectrum row is fetched
+    // from DRAM once per launch group instead of once per pair (it does not survive 64 MB of row traffic in L2)
+    const int np = rows >> log2n1;
+    const int row = AM_X_ROWORDER ? (int)(((blockIdx.x % np) << log2n1) + blockIdx.x / np) : (int)blockIdx.x;
     float2 *Ar = A + ((size_t)row << L2);
     float2 v[32];
     if constexpr (MODE != ROW_INVERSE) {
@@ -792,12 +798,15 @@ __device__ __forceinline__ void bulk_load(unsigned smem_dst, const void *gsrc, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
 }
-template <int L2>
+// MODE = ROW_FUSED (in place) or ROW_INVERSE (batch: A holds forward spectra, output to Bout; the spectrum row is an
+// L2 hit thanks to the k1-major order and is read with plain loads while the row of A waits in shared memory).
+template <int L2, int MODE>
 __global__ void __launch_bounds__(Row32Cfg<L2>::THREADS, 2)
-k_row32_stream(float2 *__restrict__ A, const float2 *__restrict__ spec, int log2n1, int rows,
+k_row32_stream(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restrict__ Bout, int log2n1, int rows,
                const float2 *__restrict__ tw, int *__restrict__ next_row) {
     typedef RegFFT<L2, 0, false, 32> F;
     typedef RegFFT<L2, 0, true, 32> I;
+    static_assert(MODE == ROW_FUSED || MODE == ROW_INVERSE, "fused or inverse-only");
     constexpr unsigned ROW_BYTES = (unsigned)sizeof(float2) << L2, PIECE = 16384;
     extern __shared__ __align__(128) float2 sm[];
     __shared__ __align__(8) unsigned long long bar_store[2];
@@ -806,6 +815,8 @@ k_row32_stream(float2 *__restrict__ A, const float2 *__restrict__ spec, int log2
     const unsigned sm_a = (unsigned)__cvta_generic_to_shared(sm);
     const unsigned bar_row = (unsigned)__cvta_generic_to_shared(&bar_store[0]);
     const unsigned bar_spec = (unsigned)__cvta_generic_to_shared(&bar_store[1]);
+    const int np = rows >> log2n1;
+    auto row_of = [&](int ticket) { return ((ticket % np) << log2n1) + ticket / np; };   // k1-major, see k_row32
     auto fetch = [&](const float2 *src, unsigned bar) {                 // one thread; the buffer must be idle
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, ROW_BYTES);
@@ -817,52 +828,71 @@ k_row32_stream(float2 *__restrict__ A, const float2 *__restrict__ spec, int log2
         mbar_init(bar_spec, 1);
     }
     __syncthreads();
-    int row = blockIdx.x;
-    if (gtid == 0 && row < rows) fetch(A + ((size_t)row << L2), bar_row);
+    int ticket = blockIdx.x;
+    if (gtid == 0 && ticket < rows) fetch(A + ((size_t)row_of(ticket) << L2), bar_row);
     unsigned parity = 0;
-    while (row < rows) {
-        float2 *Ar = A + ((size_t)row << L2);
+    while (ticket < rows) {
+        const int row = row_of(ticket);
         int claimed = 0;
         if (gtid == 0) claimed = (int)gridDim.x + atomicAdd(next_row, 1);
+        const float2 *Sr = spec + ((size_t)(row & ((1 << log2n1) - 1)) << L2);
         float2 v[32];
         AM_TL_SET(row);
         AM_TL(0);
-        mbar_wait(bar_row, parity);
-        AM_TL(1);
+        if constexpr (MODE == ROW_FUSED) {
+            mbar_wait(bar_row, parity);
+            AM_TL(1);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            int idx, t;
-            F::template in_coord<0>(gtid, j, idx, t);
-            v[j] = sm[idx];
-        }
-        if (gtid == 0) s_next = claimed;
-        __syncthreads();                                               // row copied out; the buffer becomes the exchange buffer
-        AM_TL(2);
-        const float2 *Sr = spec + ((size_t)(row & ((1 << log2n1) - 1)) << L2);
-        F::run_hook(v, sm, gtid, tw, [&] { if (gtid == 0) fetch(Sr, bar_spec); });
-        AM_TL(3);
-        mbar_wait(bar_spec, parity);
-        AM_TL(4);
+            for (int j = 0; j < 32; ++j) {
+                int idx, t;
+                F::template in_coord<0>(gtid, j, idx, t);
+                v[j] = sm[idx];
+            }
+            if (gtid == 0) s_next = claimed;
+            __syncthreads();                                           // row copied out; the buffer becomes the exchange buffer
+            AM_TL(2);
+            F::run_hook(v, sm, gtid, tw, [&] { if (gtid == 0) fetch(Sr, bar_spec); });
+            AM_TL(3);
+            mbar_wait(bar_spec, parity);
+            AM_TL(4);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            int idx, t;
-            I::template in_coord<0>(gtid, j, idx, t);                  // == F::out_coord: no exchange across the multiply
-            v[j] = amfft::cmul(v[j], sm[idx]);
+            for (int j = 0; j < 32; ++j) {
+                int idx, t;
+                I::template in_coord<0>(gtid, j, idx, t);              // == F::out_coord: no exchange across the multiply
+                v[j] = amfft::cmul(v[j], sm[idx]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {                             // spectrum row: in flight during the wait
+                int idx, t;
+                I::template in_coord<0>(gtid, j, idx, t);
+                v[j] = __ldg(&Sr[idx]);
+            }
+            mbar_wait(bar_row, parity);
+            AM_TL(4);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                int idx, t;
+                I::template in_coord<0>(gtid, j, idx, t);
+                v[j] = amfft::cmul(sm[idx], v[j]);
+            }
+            if (gtid == 0) s_next = claimed;
         }
         __syncthreads();
         AM_TL(5);
         const int next = s_next;
-        I::run_hook(v, sm, gtid, tw, [&] { if (gtid == 0 && next < rows) fetch(A + ((size_t)next << L2), bar_row); });
+        I::run_hook(v, sm, gtid, tw, [&] { if (gtid == 0 && next < rows) fetch(A + ((size_t)row_of(next) << L2), bar_row); });
         AM_TL(6);
+        float2 *Or = (MODE == ROW_INVERSE ? Bout : A) + ((size_t)row << L2);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             int idx, t;
             I::out_coord(gtid, j, idx, t);
-            Ar[idx] = v[j];
+            Or[idx] = v[j];
         }
         AM_TL(7);
         parity ^= 1;
-        row = next;
+        ticket = next;
     }
 }
 

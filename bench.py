@@ -36,9 +36,9 @@ METRIC = "audio-hours matched/sec (snippet vs stream)"
 UNIT = "audio-hours/s"
 CHUNK_S, DIST_S, PROM = 60.0, 480.0, 0.13
 # dram__bytes_read.sum + dram__bytes_write.sum per block pair at N = 2^22, from the ncu --set full capture
-# summarised in profiles/r01_ncu_full_streaming.csv (64-pair launches: k_row32 3.133 + 2.105 GB, k_col_fwd_stream
-# 0.959 + 2.092 GB, k_col_inv 2.148 + 0.459 GB in summary mode)
-NCU_DRAM_BYTES_PER_PAIR_2P22 = {"k_row": 81.8e6, "k_col_fwd": 47.7e6, "k_col_inv": 40.7e6}
+# summarised in profiles/r01_ncu_full_streaming.csv (64-pair launches: k_row32 2.181 + 2.090 GB, k_col_fwd_stream
+# 0.959 + 2.092 GB, k_col_inv 2.148 + 0.460 GB in summary mode)
+NCU_DRAM_BYTES_PER_PAIR_2P22 = {"k_row": 66.7e6, "k_col_fwd": 47.7e6, "k_col_inv": 40.8e6}
 PLANT_PERIOD_S, PLANT_JITTER_S = 600.0, 30.0
 
 

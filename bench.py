@@ -88,6 +88,35 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def bind_near_gpu(index: int):
+    """Pin this process to the CPUs next to its GPU (sysfs local_cpulist of the PCI device) so that the pinned host
+    buffer of the e2e leg is allocated on that NUMA node; returns the CPU count or None if the topology is unknown."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                      # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def plant_plan(sr, snippet_s, total_frames):
     """(offset, shift) of every planted occurrence in the global stream."""
     from oracle import am_oracle as orc
@@ -302,6 +331,7 @@ def _main(out_stream):
     # ---- end to end: PCM in pinned host memory, H2D inside the timed region
     e2e = None
     if not args.no_e2e:
+        near = bind_near_gpu(local_rank) if world > 1 else None      # several ranks share the host: keep uploads NUMA-local
         host = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=True)
         host.copy_(pcm)
         torch.cuda.synchronize()
@@ -310,7 +340,7 @@ def _main(out_stream):
         e_value = (total_frames / sr / 3600.0) / (e_ms / args.steps / 1000.0)
         verified = verified and [(p.position.start, p.snippet_id) for p in e_peaks] == starts
         e2e = {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": est["h2d_bytes"], "d2h_bytes_per_step": est["d2h_bytes"],
-               "ms_per_step": e_ms / args.steps}
+               "ms_per_step": e_ms / args.steps, "host_cpus_near_gpu": near}
         del host
 
     if rank != 0:

@@ -20,13 +20,6 @@
 #pragma once
 #include "am_fft.cuh"
 
-#ifndef AM_X_ROWSYNC
-#define AM_X_ROWSYNC 0
-#endif
-#ifndef AM_X_ROWORDER
-#define AM_X_ROWORDER 1
-#endif
-
 namespace amk {
 
 using amfft::EPT;
@@ -220,20 +213,6 @@ __device__ __forceinline__ void load_tile_fast(float2 (&v)[F::EPT], const BlockG
 // blocks are interleaved as (re, im) int16 pairs in one 32-bit word per element, and the threads then
 // pick their stage-0 inputs with conflict-free LDS.32.  Needs 16-byte aligned rows (block advance V_N
 // and segment starts multiples of 8 frames), which the host arranges; anything else takes the scalar path.
-#ifndef AM_X_L2HINT
-#define AM_X_L2HINT 0
-#endif
-__device__ __forceinline__ uint4 ldg_tile16(const void *p) {
-    uint4 r;
-#if AM_X_L2HINT == 128
-    asm volatile("ld.global.nc.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-#elif AM_X_L2HINT == 256
-    asm volatile("ld.global.nc.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-#else
-    r = __ldg((const uint4 *)p);
-#endif
-    return r;
-}
 template <class F, int LT, int L1, int THREADS>
 __device__ __forceinline__ void load_tile_i16_staged(float2 (&v)[F::EPT], const BlockGroup &g, long long f0, int log2n2,
                                                       int tid, unsigned *sraw) {
@@ -243,8 +222,8 @@ __device__ __forceinline__ void load_tile_i16_staged(float2 (&v)[F::EPT], const 
     for (int u = tid; u < (2 << L1); u += THREADS) {
         const int n1 = u >> 1, half = u & 1;
         const short *p = x + ((long long)n1 << log2n2) + half * 8;
-        const uint4 re = ldg_tile16(p);
-        const uint4 im = ldg_tile16(p + g.VN);
+        const uint4 re = __ldg((const uint4 *)p);
+        const uint4 im = __ldg((const uint4 *)(p + g.VN));
         uint4 a, b;
         a.x = __byte_perm(re.x, im.x, 0x5410); a.y = __byte_perm(re.x, im.x, 0x7632);
         a.z = __byte_perm(re.y, im.y, 0x5410); a.w = __byte_perm(re.y, im.y, 0x7632);
@@ -267,57 +246,22 @@ __device__ __forceinline__ void load_tile_i16_staged(float2 (&v)[F::EPT], const 
     __syncthreads();                                            // the buffer becomes the exchange buffer
 }
 
-// v[l * R + s] *= base * step^(l + NB * s): the thread's E = NB * R outputs k1 = q + (N1 / E) (l + NB s) form one
-// geometric sequence (two sincospif per thread instead of two per radix-R group)
-template <int R, int NB> __device__ __forceinline__ void twiddle_geo_all(float2 *v, float2 base, float2 step) {
-    using amfft::cmul;
-    constexpr int E = R * NB;
-    float2 w[E];
-    w[0] = base;
-    w[1] = cmul(base, step);
-    float2 sp = step;
-#pragma unroll
-    for (int h = 2; h < E; h <<= 1) {
-        sp = cmul(sp, sp);                         // step^h
-#pragma unroll
-        for (int i = 0; i < h; ++i) w[h + i] = cmul(w[i], sp);
-    }
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-        const int e = (i % NB) * R + i / NB;
-        v[e] = cmul(v[e], w[i]);
-    }
-}
-
 // column transform of one tile held in registers, four-step twiddle, store to A[pair][k1][n2]
 template <int L1, int LT, int E, bool TAIL_SYNC = true>
 __device__ __forceinline__ void col_fwd_finish(float2 (&v)[E], float2 *sm_all, int tid, const float2 *__restrict__ tw,
                                                int log2n2, int n2_0, float2 *__restrict__ Ap) {
     typedef RegFFT<L1, LT, false, E> F;
-#ifndef AM_X_NOFFT
     F::template run<0, TAIL_SYNC>(v, sm_all, tid, tw);
-#endif
     AM_TL(2);
     const float two_over_n = 2.0f / (float)(1u << (L1 + log2n2));
     constexpr int RB = F::bits_at(F::NST - 1), R = 1 << RB, NB = E / R;
     const int t = tid & ((1 << LT) - 1), q = tid >> LT;      // q < N1 / E
     const unsigned n2 = n2_0 + t;
-#ifndef AM_X_NOTWIDDLE
-#ifdef AM_X_GEOALL
-    // k1 = q + (N1 / E) (l + NB s)
-    twiddle_geo_all<R, NB>(v, twiddle_big(n2 * (unsigned)q, two_over_n, false),
-                           twiddle_big(n2 << (L1 - RB - (NB == 1 ? 0 : (NB == 2 ? 1 : 2))), two_over_n, false));
-#else
 #pragma unroll
     for (int l = 0; l < NB; ++l)       // k1 = q_l + s (N1 / R): W_N^{n2 k1} = W_N^{n2 q_l} (W_N^{n2 N1 / R})^s
         twiddle_geo<R>(&v[l * R], twiddle_big(n2 * (unsigned)(q + l * (F::GT >> LT)), two_over_n, false),
                        twiddle_big(n2 << (L1 - RB), two_over_n, false));
-#endif
-#endif
     AM_TL(3);
-#ifdef AM_X_NOSTORE
-    if (v[0].x != 12345.678f && v[5].y != 3.25f) return;
-#endif
 #pragma unroll
     for (int l = 0; l < NB; ++l)
 #pragma unroll
@@ -333,19 +277,12 @@ k_col_fwd(BlockGroup g, int log2n2, float2 *__restrict__ A, const float2 *__rest
     typedef ColCfg<L1, LT, E> Cfg;
     typedef RegFFT<L1, Cfg::LT, false, E> F;
     constexpr int EPT = E;
-    static_assert(EPT / (1 << F::bits_at(F::NST - 1)) <= 4, "twiddle step exponent");
     extern __shared__ float2 sm_all[];
     const int tid = threadIdx.x, pair = blockIdx.y;
     const int n2_0 = blockIdx.x << Cfg::LT;
     float2 v[EPT];
     AM_TL(0);
     const long long v0 = g.g0 + (long long)(2 * pair) * g.VN;
-#ifdef AM_X_NOLOAD
-    if (g.VN > 0) {
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) v[j] = make_float2((float)(tid + j), (float)(j * pair));
-    } else
-#endif
     if (pair_in_range(g.sv, v0, g.VN, 1ll << (L1 + log2n2), 2 * pair + 1 < g.nblocks)) {
         if (g.sv.fmt == FMT_I16_MONO) {
             const long long f0 = v0 - g.sv.lead - g.sv.buf_first + n2_0;
@@ -719,7 +656,7 @@ k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restr
     // k1-major order: consecutive CTAs take row k1 of every block pair of the group, so a spectrum row is fetched
     // from DRAM once per launch group instead of once per pair (it does not survive 64 MB of row traffic in L2)
     const int np = rows >> log2n1;
-    const int row = AM_X_ROWORDER ? (int)(((blockIdx.x % np) << log2n1) + blockIdx.x / np) : (int)blockIdx.x;
+    const int row = (int)(((blockIdx.x % np) << log2n1) + blockIdx.x / np);
     float2 *Ar = A + ((size_t)row << L2);
     float2 v[32];
     if constexpr (MODE != ROW_INVERSE) {
@@ -732,16 +669,8 @@ k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restr
         AM_TL(0);
         AM_TL_WAIT(v, 32);
         AM_TL(1);
-#ifdef AM_X_SWAP
-        I::run(v, sm, gtid, tw);
-#else
-#if AM_X_ROWSYNC == 0
         if constexpr (MODE == ROW_FUSED) F::template run<0, false>(v, sm, gtid, tw);   // the inverse's lead barrier covers it
         else F::run(v, sm, gtid, tw);
-#else
-        F::run(v, sm, gtid, tw);
-#endif
-#endif
         AM_TL(2);
         if constexpr (MODE == ROW_FORWARD) {
 #pragma unroll
@@ -763,20 +692,9 @@ k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restr
     }
     AM_TL_WAIT(v, 32);
     AM_TL(3);
-#ifdef AM_X_SWAP
-    F::run(v, sm, gtid, tw);
-#else
     // fused: the forward transform's last exchange reads must be over before the inverse writes (barrier after the
     // first inverse butterflies); nothing touches the buffer after the inverse
-#if AM_X_ROWSYNC == 0
     I::template run<0, false, MODE == ROW_FUSED>(v, sm, gtid, tw);
-#elif AM_X_ROWSYNC == 1
-    if constexpr (MODE == ROW_FUSED) __syncthreads();
-    I::run(v, sm, gtid, tw);
-#else
-    I::template run<0, false, false>(v, sm, gtid, tw);
-#endif
-#endif
     AM_TL(4);
     float2 *Or = (MODE == ROW_INVERSE) ? Bout + ((size_t)row << L2) : Ar;
 #pragma unroll

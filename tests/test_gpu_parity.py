@@ -467,6 +467,22 @@ def test_host_memory_path_equals_device_path(am, orc, full_size):
     assert st["h2d_bytes"] >= frames * 2 and len(a) > 0
 
 
+@pytest.mark.parametrize("env", [{"AM_COL_STREAM": "0"}, {"AM_ROW_STREAM": "1"}, {"AM_ROW_STREAM": "0"}])
+def test_alternate_kernel_paths(env):
+    """The kernel choices are read once per process; the non-default ones (plain-grid forward column kernel that also
+    serves windows TMA cannot describe, persistent fused row kernel, plain inverse-only row kernel of batch mode) get
+    the correlation / golden / batch / full-size-vs-oracle tests in a child process."""
+    if os.environ.get("AM_ALT_PATH_CHILD"):
+        pytest.skip("child run")
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = dict(os.environ, AM_ALT_PATH_CHILD="1", **env)
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu",
+                          "-k", "correlate_vs_oracle or golden_cases or batch_equals or full_size_chunks_vs_oracle"],
+                         cwd=root, env=child, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_c_abi_from_plain_c(am, native, tmp_path):
     """The boundary is a C ABI: compile tests/capi_smoke.c with gcc against include/ and the .so, run it."""
     import subprocess

@@ -223,6 +223,8 @@ bool launch_col_stream(am_matcher *h, const amk::BlockGroup &g, int l2, float2 *
                               (L1 == 10 && LT == 3 && E == 32 && FMT == amk::FMT_I16_MONO) ||
                               (L1 == 7 && LT == 4 && E == 16 && FMT == amk::FMT_I16_STEREO)))
         if (l2 == 13) return launch_col_stream<L1, LT, E, FMT, 13>(h, g, l2, A, grid);
+    if constexpr (L2C < 0 && L1 == 9 && LT == 4 && E == 32 && FMT == amk::FMT_I16_MONO)
+        if (l2 == 14) return launch_col_stream<L1, LT, E, FMT, 14>(h, g, l2, A, grid);     // N = 2^23 = 512 x 16384
     typedef amk::ColStreamCfg<L1, LT, E, FMT> SC;
     tl_status = AM_OK;
     if constexpr (!SC::OK) return false;
@@ -261,6 +263,13 @@ template <int L1, int LT, int E, bool INV> am_status launch_col_t(am_matcher *h,
             if (l2 == 13) {                   // N = 2^22 / 2^23 / 2^20 with 8192-point rows: column pitch known at compile time
                 TRY(set_smem(amk::k_col_inv<L1, LT, E, 13>, Cfg::SMEM_INV));
                 LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT, E, 13><<<grid, Cfg::THREADS, Cfg::SMEM_INV, h->stream>>>(g, l2, A, h->d_tw.p));
+                return AM_OK;
+            }
+        }
+        if constexpr (L1 == 9 && LT == 4 && E == 32) {
+            if (l2 == 14) {                   // N = 2^23 = 512 x 16384
+                TRY(set_smem(amk::k_col_inv<L1, LT, E, 14>, Cfg::SMEM_INV));
+                LAUNCH(h, AM_K_COL_INV, amk::k_col_inv<L1, LT, E, 14><<<grid, Cfg::THREADS, Cfg::SMEM_INV, h->stream>>>(g, l2, A, h->d_tw.p));
                 return AM_OK;
             }
         }
@@ -331,7 +340,7 @@ template <int L2, int MODE>
 am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, int l1, int rows) {
     typedef amk::RowCfg<L2> Cfg;
     static const int ept = [] { const char *v = getenv("AM_ROW_EPT"); return v && *v ? atoi(v) : 32; }();
-    if constexpr (L2 == 13 || L2 == 12) {
+    if constexpr (L2 == 13 || L2 == 12 || L2 == 14) {
         if (ept == 32) {
             typedef amk::Row32Cfg<L2> C32;
             if constexpr ((MODE == amk::ROW_FUSED || MODE == amk::ROW_INVERSE) && L2 == 13) {
@@ -383,6 +392,9 @@ constexpr int MAX_LOG2 = 24;
 void split(int log2n, int &l1, int &l2) {
     if (log2n <= SMALL_MAX_LOG2) { l1 = 0; l2 = log2n; return; }
     l2 = std::min(13, log2n - 4);
+    // 2^23 as 512 x 16384: the 512-point column kernels (16-column tiles, 32 elements per thread, run summaries) gain
+    // more than the 16384-point rows (one 512-thread CTA per SM) lose: 31.0 vs 35.7 ms per 30 h at cfg 4
+    if (log2n == 23) l2 = 14;
     const char *v = getenv("AM_ROW_LOG2");
     if (v && *v) {
         int x = atoi(v);

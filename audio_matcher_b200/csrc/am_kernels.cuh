@@ -642,7 +642,7 @@ k_row(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restric
 // this variant buys; it pays with 128 registers per thread (256 threads per row, 2 CTAs per SM).
 template <int L2> struct Row32Cfg {
     static constexpr int THREADS = (1 << L2) / 32;
-    static constexpr int MINB = 512 / THREADS;               // 128 registers per thread
+    static constexpr int MINB = THREADS >= 512 ? 1 : 512 / THREADS;      // 128 registers per thread
     static constexpr size_t SMEM = (size_t)RegFFT<L2, 0, false, 32>::SMEM_ELEMS * sizeof(float2);
 };
 template <int L2, int MODE>

@@ -54,7 +54,7 @@ def test_find_peaks_kat_through_calc_chunks(am, orc):
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("n,m,log2", [(4000, 50, 0), (4000, 50, 9), (20000, 777, 0), (25810, 4096, 14), (99538, 16384, 16),
-                                      (1574098, 262144, 20), (6292690, 480000, 22)])
+                                      (1574098, 262144, 20), (6292690, 480000, 22), (9000000, 1323000, 23)])
 def test_correlate_vs_oracle(am, orc, n, m, log2, mode):
     rng = np.random.default_rng(n + m)
     w, s = rng.standard_normal(n).astype(np.float32), rng.standard_normal(m).astype(np.float32)

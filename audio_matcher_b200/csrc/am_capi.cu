@@ -3,8 +3,9 @@
 // Host responsibilities (everything numeric runs in the CUDA kernels):
 //   * plan: overlap-save block length N, four-step split N1 x N2, segments of logical chunks
 //   * stage host-resident PCM to the device through two buffers on a copy stream
-//   * launch K2/K4/K5 (or the single-pass kernel) per group of block pairs, then the
-//     per-chunk peak kernels; one D2H of the peak list at the end
+//   * launch the column / row / column kernels (or the single-pass kernel) per group of block pairs
+//     (TMA descriptors for the persistent forward column kernel are encoded here per launch), then
+//     the per-chunk peak kernels; one D2H of the peak list at the end
 //   * calc_chunks' tail: stable sort by start + filter_surrounding/is_overshadowed
 //     (src/matcher/audio_matcher.rs:132-160) over the handful of surviving peaks
 #include <algorithm>

@@ -7,13 +7,16 @@
 //
 //   N <= 2^13 : k_small   one pass, whole transform in one thread group
 //   N >  2^13 : four-step N = N1 x N2 (element n = n1*N2 + n2, spectrum bin k = k1 + N1*k2)
-//       k_col_fwd  PCM -> f32 (scale/downmix fused into the load, mp3_reader.rs:12,35),
-//                  length-N1 column transforms over a tile of T columns, twiddle, store A[k1][n2]
-//       k_row      per row k1: length-N2 transform, multiply by the conjugate snippet
+//       k_col_fwd_stream / k_col_fwd
+//                  PCM -> f32 (scale/downmix fused into the load, mp3_reader.rs:12,35),
+//                  length-N1 column transforms over a tile of T columns, twiddle, store A[k1][n2];
+//                  the _stream version is persistent and gets the next tile's frames by TMA
+//       k_row32 / k_row (/ k_row32_stream)
+//                  per row k1: length-N2 transform, multiply by the conjugate snippet
 //                  spectrum, inverse transform, all in registers; in-place on A (for a batch of
 //                  snippets the forward transform runs once and the multiply+inverse per snippet)
-//       k_col_inv  conjugate twiddle, inverse column transforms, crop to the valid
-//                  outputs, scale by 1/(N sum s^2), store the correlation
+//       k_col_inv  conjugate twiddle (carrying the 1/(N sum s^2) scale), inverse column transforms,
+//                  crop to the valid outputs, store the correlation or its run summaries
 //
 // Replaces fftconvolve::fftcorrelate as called at src/matcher/audio_matcher.rs:305 and the
 // maths of MyConvolve::correlate (:414-457).

@@ -7,7 +7,8 @@ path lives here; decoding, tagging and the CLI stay with the reference.
 from .matcher import (Config, CudaConvolve, Mode, Peak, PeakConfig, calc_chunks, calc_chunks_sharded,  # noqa: F401
                       is_overshadowed, merge_peaks, test_data)
 from .labels import TimeLabel, print_offsets, timelabel_from_peaks, write_labels  # noqa: F401
+from .mp3_duration import claimed_samples, mp3_duration  # noqa: F401
 
 __all__ = ["Config", "CudaConvolve", "Mode", "Peak", "PeakConfig", "calc_chunks", "calc_chunks_sharded",
            "is_overshadowed", "merge_peaks", "test_data", "TimeLabel", "print_offsets", "timelabel_from_peaks",
-           "write_labels"]
+           "write_labels", "mp3_duration", "claimed_samples"]

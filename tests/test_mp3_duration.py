@@ -1,0 +1,97 @@
+"""mp3_duration mirror (src/matcher/mp3_reader.rs:68-108): frame walk, TLEN-as-seconds tag cache and
+the length claim, on synthetic MPEG frame streams (the reference's own fixture res/local/Interlude.mp3 is absent)."""
+import struct
+
+import pytest
+
+from audio_matcher_b200 import mp3_duration as md
+
+
+def _frame(bitrate_idx=9, sr_idx=0, pad=0, version=3, layer_bits=1, mono=False):
+    """One MPEG audio frame with a zero payload (default: MPEG1 Layer III, 128 kbit/s, 44.1 kHz, stereo)."""
+    b1 = 0xE0 | (version << 3) | (layer_bits << 1) | 1
+    b2 = (bitrate_idx << 4) | (sr_idx << 2) | (pad << 1)
+    b3 = 0xC0 if mono else 0x00
+    hdr = bytes([0xFF, b1, b2, b3])
+    size = md.parse_frame_header(hdr)[0]
+    return hdr + b"\x00" * (size - 4)
+
+
+def _stream(n, **kw):
+    # 44.1 kHz CBR needs a padded frame now and then; alternate to exercise both sizes
+    return b"".join(_frame(pad=i % 2, **kw) for i in range(n))
+
+
+def test_frame_header_tables():
+    assert md.parse_frame_header(_frame()[:4]) == (417, 1152, 44100, 2)
+    assert md.parse_frame_header(_frame(pad=1)[:4]) == (418, 1152, 44100, 2)
+    assert md.parse_frame_header(_frame(sr_idx=1, bitrate_idx=14, mono=True)[:4]) == (960, 1152, 48000, 1)   # 320 kbit/s
+    assert md.parse_frame_header(_frame(version=2, bitrate_idx=8)[:4]) == (208, 576, 22050, 2)               # MPEG2 L3 64k
+    assert md.parse_frame_header(_frame(layer_bits=3, bitrate_idx=4)[:4])[1] == 384                          # Layer I
+    assert md.parse_frame_header(b"\xff\xfb\xf0\x00") is None and md.parse_frame_header(b"\xff\xfb\x0c\x00") is None
+    assert md.parse_frame_header(b"ID3\x04") is None
+
+
+def test_frame_walk_counts_samples_like_the_decoder_sum():
+    n = 281                                                     # 281 * 1152 / 44100 = 7.3404 s (the Interlude-sized case)
+    secs, frames, rate = md.frame_walk(_stream(n))
+    assert frames == n and rate == 44100 and abs(secs - n * 1152 / 44100) < 1e-9
+    # junk with a false sync word in front, ID3v1 trailer behind
+    junk = b"\x00\x11\xff\xfb\x90" + b"\x22" * 20
+    secs2, frames2, _ = md.frame_walk(junk + _stream(n) + b"TAG" + b"\x00" * 125)
+    assert frames2 == n and abs(secs2 - secs) < 1e-9
+    with pytest.raises(md.NoMp3):
+        md.frame_walk(b"\x00" * 5000)
+
+
+def test_tag_cache_turns_the_duration_into_whole_seconds(tmp_path):
+    """The quirk behind `ov < m - 1`: first call 7.34 s from the frames, then TLEN = 7 is
+    stored and every later call answers 7 s (tagger.rs:176-178, :193)."""
+    p = tmp_path / "interlude.mp3"
+    p.write_bytes(_stream(281))
+    first = md.mp3_duration(p)
+    assert abs(first - 281 * 1152 / 44100) < 1e-9
+    data = p.read_bytes()
+    assert data[:3] == b"ID3" and md.read_tlen_seconds(data) == 7
+    assert md.frame_walk(data)[1] == 281                        # audio untouched behind the new tag
+    assert md.mp3_duration(p) == 7.0
+    sr = 44100
+    m = md.frame_walk(data)[1] * 1152
+    ov = round(7.0 * sr)
+    assert ov == 308700 and m - ov - 1 == 15011                 # the 15,011-offset gap per chunk boundary
+    assert md.claimed_samples(first, sr) == int(first * sr)
+
+
+def test_existing_tag_frames_survive_the_update(tmp_path):
+    def v23_frame(fid, payload):
+        return fid + struct.pack(">I", len(payload)) + b"\x00\x00" + payload
+    body = v23_frame(b"TIT2", b"\x00Interlude") + v23_frame(b"TLEN", b"\x00999") + v23_frame(b"TALB", b"\x03Album")
+    pad = 64
+    tag = b"ID3\x03\x00\x00" + md._to_synchsafe(len(body) + pad) + body + b"\x00" * pad
+    audio = _stream(50)
+    data = tag + audio
+    assert md.read_tlen_seconds(data) == 999
+    out = md.with_tlen_seconds(data, 12)
+    assert md.read_tlen_seconds(out) == 12 and len(out) == len(data)      # fits into the old padding: same layout
+    t = md._split_tag(out)
+    ids = [f[0] for f in md._frames_of(t[2], t[0])]
+    assert ids == [b"TIT2", b"TALB", b"TLEN"] and out[len(tag):] == audio
+    # a tag with a length answers without touching the file
+    p = tmp_path / "tagged.mp3"
+    p.write_bytes(out)
+    assert md.mp3_duration(p) == 12.0 and p.read_bytes() == out
+    # utf-16 text frame, v2.4 synchsafe sizes
+    body4 = b"TLEN" + md._to_synchsafe(7) + b"\x00\x00" + b"\x01" + "42".encode("utf-16")[:6]
+    assert md.read_tlen_seconds(b"ID3\x04\x00\x00" + md._to_synchsafe(len(body4)) + body4 + audio) == 42
+
+
+def test_errors(tmp_path):
+    with pytest.raises(md.NoFile):
+        md.mp3_duration(tmp_path / "missing.mp3")
+    p = tmp_path / "not.mp3"
+    p.write_bytes(b"RIFF" + b"\x00" * 4000)
+    with pytest.raises(md.NoMp3):
+        md.mp3_duration(p)
+    unsync = b"ID3\x03\x00\x80" + md._to_synchsafe(0) + _stream(3)
+    with pytest.raises(md.ID3Error):
+        md.with_tlen_seconds(unsync, 1)

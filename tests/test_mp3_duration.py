@@ -1,10 +1,11 @@
 """mp3_duration mirror (src/matcher/mp3_reader.rs:68-108): frame walk, TLEN-as-seconds tag cache and
 the length claim, on synthetic MPEG frame streams (the reference's own fixture res/local/Interlude.mp3 is absent)."""
+import importlib
 import struct
 
 import pytest
 
-from audio_matcher_b200 import mp3_duration as md
+md = importlib.import_module("audio_matcher_b200.mp3_duration")   # the package also exports the function of that name
 
 
 def _frame(bitrate_idx=9, sr_idx=0, pad=0, version=3, layer_bits=1, mono=False):

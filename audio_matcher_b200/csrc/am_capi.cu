@@ -17,6 +17,7 @@
 #include <map>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include <cuda.h>
@@ -88,6 +89,56 @@ template <class T> struct DevBuf {
 
 }  // namespace
 
+// Upload of PAGEABLE host memory (what a Vec / numpy caller hands over).  cudaMemcpyAsync stages such memory inside the
+// driver at ~11 GB/s; here a few host threads copy 32 MB chunks into a small ring of pinned buffers and each chunk
+// goes out with an asynchronous copy while the next one is being filled.  Pinned / registered memory never comes here.
+struct HostStager {
+    static constexpr size_t CHUNK = (size_t)32 << 20;
+    static constexpr int SLOTS = 3;
+    void *pinned[SLOTS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[SLOTS] = {nullptr, nullptr, nullptr};
+    bool busy[SLOTS] = {false, false, false};
+    bool ensure() {
+        for (int i = 0; i < SLOTS; ++i) {
+            if (!pinned[i] && cudaHostAlloc(&pinned[i], CHUNK, cudaHostAllocDefault) != cudaSuccess) { pinned[i] = nullptr; cudaGetLastError(); return false; }
+            if (!ev[i] && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { ev[i] = nullptr; cudaGetLastError(); return false; }
+        }
+        return true;
+    }
+    static void parallel_copy(void *dst, const void *src, size_t n, int threads) {
+        if (threads <= 1 || n < ((size_t)4 << 20)) { memcpy(dst, src, n); return; }
+        const size_t per = ((n / threads + 4095) / 4096) * 4096;
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; ++t) {
+            const size_t o = per * t;
+            if (o >= n) break;
+            pool.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, std::min(per, n - o)); });
+        }
+        memcpy(dst, src, std::min(per, n));
+        for (auto &th : pool) th.join();
+    }
+    cudaError_t upload(void *dst_dev, const void *src, size_t bytes, cudaStream_t s, int threads) {
+        int slot = 0;
+        for (size_t o = 0; o < bytes; o += CHUNK, slot = (slot + 1) % SLOTS) {
+            const size_t n = std::min(CHUNK, bytes - o);
+            cudaError_t e;
+            if (busy[slot] && (e = cudaEventSynchronize(ev[slot])) != cudaSuccess) return e;
+            parallel_copy(pinned[slot], (const char *)src + o, n, threads);
+            if ((e = cudaMemcpyAsync((char *)dst_dev + o, pinned[slot], n, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(ev[slot], s)) != cudaSuccess) return e;
+            busy[slot] = true;
+        }
+        return cudaSuccess;
+    }
+    void release() {
+        for (int i = 0; i < SLOTS; ++i) {
+            if (ev[i]) { if (busy[i]) cudaEventSynchronize(ev[i]); cudaEventDestroy(ev[i]); ev[i] = nullptr; }
+            if (pinned[i]) { cudaFreeHost(pinned[i]); pinned[i] = nullptr; }
+            busy[i] = false;
+        }
+    }
+};
+
 struct am_matcher {
     std::mutex mu;
     int device = 0;
@@ -111,6 +162,7 @@ struct am_matcher {
     DevBuf<amp::DevPeak> d_peaks;
     DevBuf<unsigned long long> d_count;   // [0] = count, [1] low 32 bits = flags
     DevBuf<unsigned char> d_stage[2];
+    HostStager stager;                      // pageable host streams only
     am_stats stats;
     // optional per-kernel-class device timing (cudaEvent pairs around every launch)
     bool profiling = false;
@@ -720,7 +772,7 @@ void am_matcher_destroy(am_matcher *h) {
     for (auto &kv : h->spectra) cudaFree(kv.second);
     h->d_snip.release(); h->d_tw.release(); h->d_A.release(); h->d_B.release(); h->d_c.release(); h->d_tmin.release();
     h->d_tmax.release(); h->d_rsum.release(); h->d_peaks.release(); h->d_count.release(); h->d_sched.release();
-    h->d_stage[0].release(); h->d_stage[1].release();
+    h->d_stage[0].release(); h->d_stage[1].release(); h->stager.release();
     for (int i = 0; i < 2; ++i) {
         if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -959,6 +1011,18 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     const float theta = 0.5f * h->cfg.prominence;
     unsigned long long cnt[2] = {0, 0};
 
+    // pageable host stream: copy through our own pinned ring with a few threads (AM_STAGE_THREADS, 0 = leave it to the driver)
+    int stage_threads = 0;
+    if (mem == AM_MEM_HOST) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, stream) == cudaSuccess && pa.type == cudaMemoryTypeUnregistered) {
+            static const int env = [] { const char *v = getenv("AM_STAGE_THREADS"); return v && *v ? atoi(v) : -1; }();
+            const int hw = (int)std::thread::hardware_concurrency();
+            stage_threads = env >= 0 ? env : std::max(1, std::min(8, hw / 4));
+        }
+        cudaGetLastError();
+    }
+
     // one pass over all segments: transforms + peak kernels; the counters come back in cnt
     auto run_pass = [&](bool sum) -> am_status {
         CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
@@ -978,8 +1042,11 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
                 const size_t bytes = (size_t)(f_hi - f_lo) * fb;
                 CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // kernels that read this buffer are done
                 TRY(h->d_stage[b].reserve(bytes));
-                CU(cudaMemcpyAsync(h->d_stage[b].p, (const unsigned char *)stream + (size_t)(f_lo - (long long)buf_first_frame) * fb,
-                                   bytes, cudaMemcpyHostToDevice, h->copy_stream));
+                const unsigned char *src = (const unsigned char *)stream + (size_t)(f_lo - (long long)buf_first_frame) * fb;
+                if (stage_threads > 0 && bytes >= ((size_t)64 << 20) && h->stager.ensure())
+                    CU(h->stager.upload(h->d_stage[b].p, src, bytes, h->copy_stream, stage_threads));
+                else
+                    CU(cudaMemcpyAsync(h->d_stage[b].p, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
                 CU(cudaEventRecord(h->ev_up[b], h->copy_stream));
                 CU(cudaStreamWaitEvent(h->stream, h->ev_up[b], 0));
                 h->stats.h2d_bytes += bytes;

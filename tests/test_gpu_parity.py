@@ -465,6 +465,10 @@ def test_host_memory_path_equals_device_path(am, orc, full_size):
     for x, y in zip(a, b):
         assert abs(x.height - y.height) <= 1e-5 * abs(y.height) and abs(x.prominence - y.prominence) <= 1e-5 * abs(y.prominence)
     assert st["h2d_bytes"] >= frames * 2 and len(a) > 0
+    # pageable host memory (numpy): goes through the library's pinned ring filled by host threads
+    pageable = fs["pcm"][:frames].cpu().numpy()
+    c = am.calc_chunks(fs["sr"], pageable, fs["algo"], True, fs["conf"])
+    assert [(p.position.start, p.height, p.prominence) for p in c] == [(p.position.start, p.height, p.prominence) for p in a]
 
 
 @pytest.mark.parametrize("env", [{"AM_COL_STREAM": "0"}, {"AM_ROW_STREAM": "1"}, {"AM_ROW_STREAM": "0"}])

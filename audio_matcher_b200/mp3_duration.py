@@ -13,8 +13,13 @@ that `calc_chunks` reproduces (tests/test_gpu_parity.py, oracle golden cases).
 
 Steps 2 and 3 are one frame-header walk here: every MPEG audio frame carries a fixed number of samples per
 channel (384 / 1152 / 576 by layer and version), so `sum(samples_per_frame / sample_rate)` is what the decode
-sums.  Parity unpinned: the reference's only test for this function needs `res/local/Interlude.mp3`, which is
-not in the repository; an `Info`/`Xing` header frame is counted like any other frame.
+sums (an `Info`/`Xing` header frame is counted like any other frame).
+
+Pinned on the reference's own fixture `res/id3test.mp3` (tests/golden/mp3_duration.json, made by
+tests/golden/make_mp3_golden.py): the tag reading is the 7 s that `tagger.rs:791` asserts, and the frame walk finds
+281 frames = 323,712 samples = 7.34 s, i.e. the `as_secs() == 7` of `short_mp3_duration` (mp3_reader.rs:112-121; that
+test names `res/local/Interlude.mp3`, which is absent, but SURVEY.md 8a gives the same 323,712 samples for it).  What
+stays unpinned is the `mp3-duration` crate's treatment of VBR headers (step 2), which no reference test exercises.
 """
 from __future__ import annotations
 

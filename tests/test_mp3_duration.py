@@ -1,6 +1,8 @@
 """mp3_duration mirror (src/matcher/mp3_reader.rs:68-108): frame walk, TLEN-as-seconds tag cache and
 the length claim, on synthetic MPEG frame streams (the reference's own fixture res/local/Interlude.mp3 is absent)."""
 import importlib
+import json
+import os
 import struct
 
 import pytest
@@ -96,3 +98,44 @@ def test_errors(tmp_path):
     unsync = b"ID3\x03\x00\x80" + md._to_synchsafe(0) + _stream(3)
     with pytest.raises(md.ID3Error):
         md.with_tlen_seconds(unsync, 1)
+
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "mp3_duration.json")
+REF_FIXTURE = "/root/reference/res/id3test.mp3"
+
+
+def test_golden_values_match_the_reference_expectations():
+    """tests/golden/mp3_duration.json was produced from the reference's fixture res/id3test.mp3: the tag reading must be
+    the 7 s the reference's tagger test expects (tagger.rs:791), the frame walk must truncate to the 7 s its
+    mp3_duration test expects (mp3_reader.rs:112-121) and give the 323,712-sample snippet of SURVEY.md 8a row 5."""
+    with open(GOLD) as f:
+        g = json.load(f)
+    assert g["tlen_seconds"] == g["reference_expectation"]["tagger.rs:791 Length"] == 7
+    assert int(g["seconds"]) == g["reference_expectation"]["mp3_reader.rs:112-121 as_secs"] == 7
+    assert g["frames"] == 281 and g["sample_rate"] == 44100 and g["samples"] == 323712
+    assert round(7.0 * 44100) == 308700 and g["samples"] - 308700 - 1 == 15011
+    assert "TLEN" in g["frame_ids"] and g["id3_major"] == 3
+
+
+@pytest.mark.skipif(not os.path.exists(REF_FIXTURE), reason="reference fixture only exists in the build container")
+def test_mirror_on_the_reference_fixture(tmp_path):
+    with open(GOLD) as f:
+        g = json.load(f)
+    data = open(REF_FIXTURE, "rb").read()
+    assert len(data) == g["bytes"] and md.read_tlen_seconds(data) == g["tlen_seconds"]
+    secs, frames, rate = md.frame_walk(data)
+    assert (frames, rate) == (g["frames"], g["sample_rate"]) and abs(secs - g["seconds"]) < 1e-12
+    p = tmp_path / "copy.mp3"
+    p.write_bytes(data)
+    assert md.mp3_duration(p) == 7.0 and p.read_bytes() == data          # tagged: answered from the tag, file untouched
+    # drop the length from the tag -> the frames answer, and the answer is cached as whole seconds
+    t = md._split_tag(data)
+    frames_wo = [f for f in md._frames_of(t[2], t[0]) if f[0] != b"TLEN"]
+    body = b"".join(fid + struct.pack(">I", len(pl)) + fl + pl for fid, fl, pl in frames_wo)
+    room = g["id3_extent"] - 10
+    stripped = b"ID3\x03\x00\x00" + md._to_synchsafe(room) + body + b"\x00" * (room - len(body)) + data[g["id3_extent"]:]
+    p.write_bytes(stripped)
+    assert abs(md.mp3_duration(p) - g["seconds"]) < 1e-12
+    again = p.read_bytes()
+    assert md.read_tlen_seconds(again) == 7 and again[g["id3_extent"]:] == data[g["id3_extent"]:] and len(again) == len(data)
+    assert md.mp3_duration(p) == 7.0

@@ -16,6 +16,8 @@
 //   fn calc_chunks(sr, m_samples, algo, scale, config)     :88-141 audio_matcher::calc_chunks(sr, samples, algo, scale, config)
 //   fn is_overshadowed(element, other, sr, max_distance)   :143-160 audio_matcher::is_overshadowed(...)
 //   fn test_data(range)                                    :481-483 audio_matcher::test_data(from, to)
+//   print_offsets / start_as_duration      src/matcher/mod.rs:110-129 audio_matcher::offset_lines / start_as_duration
+//   timelabel_from_peaks                 src/archive/data.rs:87-107 audio_matcher::timelabel_from_peaks, TimeLabel
 //
 // Error behaviour: the reference returns Result<_, Box<dyn Error>> from correlate_with_sample and panics (unwrap,
 // :122) inside calc_chunks; here every failing C-ABI call throws audio_matcher::Error carrying am_last_error().
@@ -24,6 +26,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -156,6 +159,56 @@ inline bool is_overshadowed(const Peak &element, const Peak *other, uint32_t sr,
     if (!other) return false;
     const am_peak e = element.raw(), o = other->raw();
     return am_is_overshadowed(&e, &o, sr, max_distance_s) != 0;
+}
+
+// ---- output side of the path: what matcher::run does with the peaks (src/matcher/mod.rs:85-99) ----------------
+
+// start_as_duration, src/matcher/mod.rs:127-129 (seconds)
+inline double start_as_duration(const Peak &peak, uint32_t sr) { return (double)peak.start / (double)sr; }
+
+// the log lines of print_offsets, src/matcher/mod.rs:110-125
+inline std::vector<std::string> offset_lines(const std::vector<Peak> &peaks, uint32_t sr) {
+    std::vector<std::string> out;
+    if (peaks.empty()) out.push_back("no offsets found");
+    for (std::size_t i = 0; i < peaks.size(); ++i) {
+        const unsigned long long secs = (unsigned long long)start_as_duration(peaks[i], sr);
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "Offset %zu: %02llu:%02llu:%02llu with prominence %g", i + 1, secs / 3600, (secs / 60) % 60,
+                      secs % 60, (double)peaks[i].prominence.value_or(0.f));
+        out.push_back(buf);
+    }
+    return out;
+}
+
+// audacity TimeLabel as matcher::run writes it: start<TAB>end<TAB>name
+struct TimeLabel {
+    double start = 0.0, end = 0.0;
+    std::string name;
+    std::string line() const {
+        char buf[96];
+        std::snprintf(buf, sizeof buf, "%.6f\t%.6f\t", start, end);
+        return std::string(buf) + name;
+    }
+};
+
+// timelabel_from_peaks, src/archive/data.rs:87-107: consecutive peak pairs -> a label from delay_start after a
+// peak to the next peak, numbered from 1 ('#' in the pattern is replaced by the number)
+inline std::vector<TimeLabel> timelabel_from_peaks(const std::vector<Peak> &peaks, uint32_t sr, double delay_start_s = 7.0,
+                                                   const std::string &name_pattern = "Segment #") {
+    std::vector<TimeLabel> out;
+    for (std::size_t i = 0; i + 1 < peaks.size(); ++i) {
+        TimeLabel l;
+        l.start = start_as_duration(peaks[i], sr) + delay_start_s;
+        l.end = start_as_duration(peaks[i + 1], sr);
+        l.name = name_pattern;
+        for (std::size_t pos = 0; (pos = l.name.find('#', pos)) != std::string::npos;) {
+            const std::string num = std::to_string(i + 1);
+            l.name.replace(pos, 1, num);
+            pos += num.size();
+        }
+        out.push_back(l);
+    }
+    return out;
 }
 
 // test_data, audio_matcher.rs:481-483

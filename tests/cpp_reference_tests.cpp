@@ -73,8 +73,22 @@ static void correlate_kat() {
     ASSERT(algo.correlate_with_sample(test_data(-10, 10), Mode::Same, false).size() == 20);
 }
 
+// output side (src/matcher/mod.rs:110-129, src/archive/data.rs:87-107); same expectations as tests/test_host_logic.py
+static void labels_and_offsets() {
+    std::vector<Peak> peaks = {peak(21 * 100, 0.9f), peak(1003 * 100, 0.5f), peak(4000 * 100, 0.7f)};
+    const auto labels = timelabel_from_peaks(peaks, 100);
+    ASSERT(labels.size() == 2);
+    ASSERT(labels[0].start == 28.0 && labels[0].end == 1003.0 && labels[0].name == "Segment 1");
+    ASSERT(labels[1].start == 1010.0 && labels[1].end == 4000.0 && labels[1].name == "Segment 2");
+    ASSERT(labels[0].line() == "28.000000\t1003.000000\tSegment 1");
+    ASSERT(offset_lines(peaks, 100)[1] == "Offset 2: 00:16:43 with prominence 0.5");
+    ASSERT(offset_lines({}, 100).size() == 1 && offset_lines({}, 100)[0] == "no offsets found");
+    ASSERT(timelabel_from_peaks({peak(5, 1.f)}, 1).empty());
+}
+
 int main() {
     const bool gpu = am_device_count() > 0;
+    labels_and_offsets();
     if (!gpu) {
         bool threw = false;
         try {

@@ -23,7 +23,10 @@ FMT_F32_MONO, FMT_I16_MONO, FMT_I16_STEREO = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a",
-              "-lineinfo", "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "128"]
+              "-lineinfo", "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "128", "-ldl"]
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t)
+COMM_ID_BYTES = 128
+ABI_VERSION = 2
 
 
 class AmConfig(C.Structure):
@@ -42,7 +45,7 @@ class AmStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("fft_blocks", C.c_uint64), ("frames", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("fft_log2", C.c_uint32),
                 ("log2_n1", C.c_uint32), ("log2_n2", C.c_uint32), ("chunks", C.c_uint32),
-                ("summary_mode", C.c_uint32), ("reserved", C.c_uint32)]
+                ("summary_mode", C.c_uint32), ("dense_chunks", C.c_uint32)]
 
 
 class AmKernelTime(C.Structure):
@@ -67,11 +70,21 @@ SYMBOLS = {
     "am_matcher_get_stats": (C.c_int, [_VP, C.POINTER(AmStats)]),
     "am_matcher_set_profiling": (C.c_int, [_VP, C.c_int]),
     "am_matcher_get_kernel_times": (C.c_int, [_VP, C.POINTER(AmKernelTime), _SZ, C.POINTER(_SZ)]),
+    "am_matcher_set_progress": (C.c_int, [_VP, _VP, _VP]),
     "am_inverse_sample_auto_correlation": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "am_out_len": (_SZ, [_SZ, _SZ, C.c_int]),
     "am_correlate": (C.c_int, [_VP, _VP, _SZ, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _SZ, C.c_int,
                                C.POINTER(_SZ)]),
     "am_num_chunks": (_SZ, [_VP, _SZ]),
+    "am_chunk_geometry": (C.c_int, [_VP, C.POINTER(_SZ), C.POINTER(_SZ)]),
+    "am_shard_frames": (C.c_int, [_VP, _SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ)]),
+    "am_comm_get_unique_id": (C.c_int, [_VP]),
+    "am_comm_init": (C.c_int, [C.c_int, C.c_int, _VP, C.POINTER(_VP)]),
+    "am_comm_destroy": (None, [_VP]),
+    "am_comm_rank": (C.c_int, [_VP]),
+    "am_comm_size": (C.c_int, [_VP]),
+    "am_calc_chunks_sharded": (C.c_int, [_VP, _VP, _VP, _SZ, _SZ, _SZ, C.c_int, C.c_int, C.c_int, _SZ, _SZ,
+                                         C.POINTER(AmPeak), _SZ, C.POINTER(_SZ)]),
     "am_calc_chunks": (C.c_int, [_VP, _VP, _SZ, C.c_int, C.c_int, C.c_int, C.POINTER(AmPeak), _SZ, C.POINTER(_SZ)]),
     "am_calc_chunks_range": (C.c_int, [_VP, _VP, _SZ, _SZ, _SZ, C.c_int, C.c_int, C.c_int, _SZ, _SZ, C.c_int,
                                        C.POINTER(AmPeak), _SZ, C.POINTER(_SZ)]),

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include <cuda.h>
+#include <dlfcn.h>
 
 #include "../../include/audio_matcher.h"
 #include "am_kernels.cuh"
@@ -158,11 +159,14 @@ struct am_matcher {
     std::map<int, float2 *> spectra;         // log2n -> [S][N] conjugate spectra
     DevBuf<float2> d_A, d_B;
     DevBuf<float> d_c, d_tmin, d_tmax;
-    DevBuf<float4> d_rsum;                   // summary mode: one record per aligned run of 16 outputs
+    DevBuf<float2> d_rsum;                   // summary mode: {min, max} and {first, last} per aligned run of 16 outputs (two arrays)
     DevBuf<amp::DevPeak> d_peaks;
     DevBuf<unsigned long long> d_count;   // [0] = count, [1] low 32 bits = flags
     DevBuf<unsigned char> d_stage[2];
     HostStager stager;                      // pageable host streams only
+    DevBuf<unsigned char> d_gsend, d_grecv; // multi-GPU: fixed-size peak records for the all-gather
+    am_progress_fn progress = nullptr;      // optional, fired from the calling thread
+    void *progress_user = nullptr;
     am_stats stats;
     // optional per-kernel-class device timing (cudaEvent pairs around every launch)
     bool profiling = false;
@@ -539,7 +543,7 @@ am_status get_spectrum(am_matcher *h, int log2n, float2 **out) {
 // With several snippets the stream-side work (column pass + forward row pass) is done once per block
 // group and only the multiply + inverse passes run per snippet.
 am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0, long long g1, int log2n, int scale,
-                          float *c, size_t c_stride, long long c_g0, size_t s0, size_t ns, float4 *rsum = nullptr,
+                          float *c, size_t c_stride, long long c_g0, size_t s0, size_t ns, amp::RunRecs rsum = amp::RunRecs{nullptr, nullptr},
                           float theta = 0.f) {
     if (g1 <= g0 || ns == 0) return AM_OK;
     const float inv_n = (float)(1.0 / (double)(1ull << log2n));
@@ -589,7 +593,7 @@ am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0
             TRY(launch_row<amk::ROW_FORWARD>(h, l2, h->d_A.p, nullptr, nullptr, l1, rows));
             for (size_t j = 0; j < ns; ++j) {
                 g.c = c + j * c_stride; g.scalar = scalar_of(s0 + j);
-                if (rsum) g.rsum = rsum + j * (c_stride >> 4);
+                if (rsum.mm) g.rsum = rsum.offset((long long)(j * (c_stride >> 4)));
                 TRY(launch_row<amk::ROW_INVERSE>(h, l2, h->d_A.p, spec_all + (s0 + j) * (size_t)N, h->d_B.p, l1, rows));
                 TRY(launch_col<true>(h, l1, g, l2, h->d_B.p));
             }
@@ -772,7 +776,7 @@ void am_matcher_destroy(am_matcher *h) {
     for (auto &kv : h->spectra) cudaFree(kv.second);
     h->d_snip.release(); h->d_tw.release(); h->d_A.release(); h->d_B.release(); h->d_c.release(); h->d_tmin.release();
     h->d_tmax.release(); h->d_rsum.release(); h->d_peaks.release(); h->d_count.release(); h->d_sched.release();
-    h->d_stage[0].release(); h->d_stage[1].release(); h->stager.release();
+    h->d_stage[0].release(); h->d_stage[1].release(); h->stager.release(); h->d_gsend.release(); h->d_grecv.release();
     for (int i = 0; i < 2; ++i) {
         if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -798,7 +802,15 @@ am_status am_matcher_set_config(am_matcher *h, const am_config *cfg) {
 }
 am_status am_matcher_get_stats(const am_matcher *h, am_stats *out) {
     if (!h || !out) return fail(AM_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(const_cast<am_matcher *>(h)->mu);
     *out = h->stats;
+    return AM_OK;
+}
+am_status am_matcher_set_progress(am_matcher *h, am_progress_fn fn, void *user) {
+    if (!h) return fail(AM_ERR_INVALID, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->progress = fn;
+    h->progress_user = user;
     return AM_OK;
 }
 
@@ -831,6 +843,7 @@ am_status am_matcher_get_kernel_times(const am_matcher *h, am_kernel_time *out, 
 
 am_status am_inverse_sample_auto_correlation(am_matcher *h, float *out) {
     if (!h || !out) return fail(AM_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
     *out = h->inv_ac[h->active];
     return AM_OK;
 }
@@ -889,6 +902,29 @@ size_t am_num_chunks(const am_matcher *h, size_t frames) {
     return (frames + (size_t)C - 1) / (size_t)C;          // chunked(C + ov, C), audio_matcher.rs:104
 }
 
+am_status am_chunk_geometry(const am_matcher *h, size_t *chunk, size_t *overlap) {
+    if (!h) return fail(AM_ERR_INVALID, "NULL handle");
+    long long C, ov;
+    chunk_params(h, C, ov);
+    if (chunk) *chunk = (size_t)std::max<long long>(C, 0);
+    if (overlap) *overlap = (size_t)std::max<long long>(ov, 0);
+    return AM_OK;
+}
+
+am_status am_shard_frames(const am_matcher *h, size_t total_frames, size_t first_chunk, size_t num_chunks, size_t *lo,
+                          size_t *hi) {
+    if (!h || !lo || !hi) return fail(AM_ERR_INVALID, "NULL argument");
+    long long C, ov;
+    chunk_params(h, C, ov);
+    if (C <= 0) return fail(AM_ERR_INVALID, "chunk size rounds to 0 samples");
+    const size_t total_chunks = am_num_chunks(h, total_frames);
+    if (first_chunk >= total_chunks || num_chunks == 0) { *lo = *hi = std::min((size_t)C * first_chunk, total_frames); return AM_OK; }
+    num_chunks = std::min(num_chunks, total_chunks - first_chunk);
+    *lo = (size_t)C * first_chunk;
+    *hi = std::min(total_frames, (size_t)C * (first_chunk + num_chunks) + (size_t)std::max<long long>(ov, 0));
+    return AM_OK;
+}
+
 int am_is_overshadowed(const am_peak *element, const am_peak *other, uint32_t sr, double max_distance_s) {
     if (!element || !other) return 0;                      // None never overshadows, audio_matcher.rs:149
     uint64_t e = start_ns(element->start, sr), b = start_ns(other->start, sr);
@@ -921,15 +957,16 @@ am_status am_merge_peaks(am_peak *peaks, size_t n, uint32_t sr, double distance_
     return AM_OK;
 }
 
-am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_first_frame, size_t buf_frames,
-                               size_t total_frames, am_sample_fmt fmt, am_mem mem, int scale, size_t first_chunk,
-                               size_t num_chunks, int final_filter, am_peak *out, size_t cap, size_t *n_out) {
-    if (!h || !n_out) return fail(AM_ERR_INVALID, "NULL argument");
+// The per-rank part of calc_chunks: correlation + per-chunk peak kernels for logical chunks
+// [first_chunk, first_chunk + num_chunks).  The peaks stay in h->d_peaks (unordered), *count_out of them.
+// The caller holds h->mu.
+static am_status range_pass_device(am_matcher *h, const void *stream, size_t buf_first_frame, size_t buf_frames,
+                                   size_t total_frames, am_sample_fmt fmt, am_mem mem, int scale, size_t first_chunk,
+                                   size_t num_chunks, unsigned long long *count_out) {
+    *count_out = 0;
     if ((int)fmt < 0 || (int)fmt > 2) return fail(AM_ERR_INVALID, "bad sample format");
-    std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     memset(&h->stats, 0, sizeof h->stats);
-    *n_out = 0;
     long long C, ov;
     chunk_params(h, C, ov);
     const long long L = (long long)total_frames, m = (long long)h->m;
@@ -990,7 +1027,9 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     K = std::min<long long>(K, (long long)num_chunks);
     const long long seg_c_len = ((K * C + std::max<long long>(ov - m + 1, 0) + 1 + 15) / 16) * 16;   // float4 / run alignment per snippet
     TRY(h->d_c.reserve((size_t)seg_c_len * S));
-    if (summary) TRY(h->d_rsum.reserve(((size_t)seg_c_len * S) >> 4));
+    const size_t seg_runs = ((size_t)seg_c_len * S) >> 4;
+    if (summary) TRY(h->d_rsum.reserve(2 * seg_runs));
+    const amp::RunRecs recs{h->d_rsum.p, h->d_rsum.p ? h->d_rsum.p + seg_runs : nullptr}, no_recs{nullptr, nullptr};
     const long long tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
     TRY(h->d_tmin.reserve((size_t)(K * tiles_stride) * S));
     TRY(h->d_tmax.reserve((size_t)(K * tiles_stride) * S));
@@ -1055,21 +1094,22 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
                 sv.x = stream; sv.buf_first = (long long)buf_first_frame; sv.buf_frames = (long long)buf_frames;
             }
             TRY(run_correlation(h, sv, g0, g1, log2n, scale, h->d_c.p, (size_t)seg_c_len, g0, 0, S,
-                                sum ? h->d_rsum.p : nullptr, theta));
+                                sum ? recs : no_recs, theta));
             if (mem == AM_MEM_HOST) CU(cudaEventRecord(h->ev_done[seg_idx & 1], h->stream));
+            if (h->progress) h->progress(h->progress_user, 0, (size_t)i0, (size_t)(i1 - i0));
             amp::ChunkGeom cg;
             cg.C = C; cg.ov = ov; cg.m = m; cg.total = L; cg.first_chunk = i0; cg.c_g0 = g0; cg.tiles_stride = (int)tiles_stride;
             cg.c_stride = seg_c_len; cg.seg_end = g1 - g0;
             dim3 tgrid3((unsigned)((tiles_stride + 7) / 8), (unsigned)(i1 - i0), (unsigned)S), pgrid((unsigned)(i1 - i0), (unsigned)S);
             if (sum) {
-                LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(h->d_rsum.p, cg, h->d_tmin.p, h->d_tmax.p, po.flags));
+                LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(recs, cg, h->d_tmin.p, h->d_tmax.p, po.flags));
                 LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<true><<<pgrid, 256, pk_smem, h->stream>>>(
-                                                h->d_c.p, h->d_rsum.p, theta, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist,
+                                                h->d_c.p, recs, theta, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist,
                                                 pk_cap, sm_tiles, po));
             } else {
                 LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid3, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p));
                 LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<false><<<pgrid, 256, pk_smem, h->stream>>>(
-                                                h->d_c.p, nullptr, 0.f, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist,
+                                                h->d_c.p, no_recs, 0.f, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist,
                                                 pk_cap, sm_tiles, po));
             }
         }
@@ -1090,10 +1130,23 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     if ((unsigned)cnt[1] & 1u)
         return fail(AM_ERR_CAPACITY, "a chunk produced more than max_peaks_per_chunk = %d peak candidates (raise it or the prominence)", pk_cap);
     if (cnt[0] > dev_cap) return fail(AM_ERR_CAPACITY, "%llu peaks exceed the device list capacity %zu", cnt[0], dev_cap);
-    std::vector<am_peak> all((size_t)cnt[0]);
-    if (cnt[0]) {
-        CU(cudaMemcpy(all.data(), h->d_peaks.p, (size_t)cnt[0] * sizeof(am_peak), cudaMemcpyDeviceToHost));
-        h->stats.d2h_bytes += (size_t)cnt[0] * sizeof(am_peak);
+    *count_out = cnt[0];
+    if (h->progress) h->progress(h->progress_user, 1, first_chunk, num_chunks);
+    return AM_OK;
+}
+
+am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_first_frame, size_t buf_frames,
+                               size_t total_frames, am_sample_fmt fmt, am_mem mem, int scale, size_t first_chunk,
+                               size_t num_chunks, int final_filter, am_peak *out, size_t cap, size_t *n_out) {
+    if (!h || !n_out) return fail(AM_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    *n_out = 0;
+    unsigned long long count = 0;
+    TRY(range_pass_device(h, stream, buf_first_frame, buf_frames, total_frames, fmt, mem, scale, first_chunk, num_chunks, &count));
+    std::vector<am_peak> all((size_t)count);
+    if (count) {
+        CU(cudaMemcpy(all.data(), h->d_peaks.p, (size_t)count * sizeof(am_peak), cudaMemcpyDeviceToHost));
+        h->stats.d2h_bytes += (size_t)count * sizeof(am_peak);
     }
     if (!final_filter) {
         std::stable_sort(all.begin(), all.end(), [](const am_peak &a, const am_peak &b) {
@@ -1139,7 +1192,8 @@ am_status am_debug_peaks_from_correlation(am_matcher *h, const float *c_host, si
     const long long nchunks = (L + C - 1) / C;
     const long long seg_c_len = (((long long)n + 15) / 16) * 16;
     TRY(h->d_c.reserve((size_t)seg_c_len));
-    TRY(h->d_rsum.reserve((size_t)seg_c_len >> 4));
+    TRY(h->d_rsum.reserve(2 * ((size_t)seg_c_len >> 4)));
+    const amp::RunRecs recs{h->d_rsum.p, h->d_rsum.p + ((size_t)seg_c_len >> 4)}, no_recs{nullptr, nullptr};
     const long long tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
     TRY(h->d_tmin.reserve((size_t)(nchunks * tiles_stride)));
     TRY(h->d_tmax.reserve((size_t)(nchunks * tiles_stride)));
@@ -1170,13 +1224,13 @@ am_status am_debug_peaks_from_correlation(am_matcher *h, const float *c_host, si
         CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
         CU(cudaMemcpyAsync(h->d_c.p, c_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         if (sum) {
-            amp::k_debug_make_runs<<<(unsigned)(((seg_c_len >> 4) + 255) / 256), 256, 0, h->stream>>>(h->d_c.p, (long long)n, theta, h->d_rsum.p);
-            amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(h->d_rsum.p, cg, h->d_tmin.p, h->d_tmax.p, po.flags);
-            amp::k_chunk_peaks<true><<<pgrid, 256, pk_smem, h->stream>>>(h->d_c.p, h->d_rsum.p, theta, cg, h->d_tmin.p, h->d_tmax.p,
+            amp::k_debug_make_runs<<<(unsigned)(((seg_c_len >> 4) + 255) / 256), 256, 0, h->stream>>>(h->d_c.p, (long long)n, theta, recs);
+            amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(recs, cg, h->d_tmin.p, h->d_tmax.p, po.flags);
+            amp::k_chunk_peaks<true><<<pgrid, 256, pk_smem, h->stream>>>(h->d_c.p, recs, theta, cg, h->d_tmin.p, h->d_tmax.p,
                                                                        h->cfg.prominence, min_dist, pk_cap, sm_tiles, po);
         } else {
             amp::k_tile_minmax<<<tgrid3, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p);
-            amp::k_chunk_peaks<false><<<pgrid, 256, pk_smem, h->stream>>>(h->d_c.p, nullptr, 0.f, cg, h->d_tmin.p, h->d_tmax.p,
+            amp::k_chunk_peaks<false><<<pgrid, 256, pk_smem, h->stream>>>(h->d_c.p, no_recs, 0.f, cg, h->d_tmin.p, h->d_tmax.p,
                                                                         h->cfg.prominence, min_dist, pk_cap, sm_tiles, po);
         }
         CU(cudaGetLastError());
@@ -1195,6 +1249,163 @@ am_status am_debug_peaks_from_correlation(am_matcher *h, const float *c_host, si
     *n_out = all.size();
     if (all.size() > cap) return fail(AM_ERR_CAPACITY, "%zu peaks, capacity %zu", all.size(), cap);
     if (!all.empty()) memcpy(out, all.data(), all.size() * sizeof(am_peak));
+    return AM_OK;
+}
+
+// ---- multi-GPU merge over NCCL ------------------------------------------------------------------------
+// NCCL is bound at run time: the handful of entry points used here have had the same C signatures through
+// NCCL 2.x, and a process that already holds a copy (torch.distributed) must share it rather than get a second one.
+namespace {
+struct NcclId { char internal[AM_COMM_ID_BYTES]; };
+typedef struct ncclComm *nccl_comm_t;
+struct NcclApi {
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(nccl_comm_t *, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    char why[256] = "";
+};
+NcclApi &nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        const char *names[] = {getenv("AM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        void *lib = nullptr;
+        for (const char *n : names) {
+            if (!n || !*n) continue;
+            // RTLD_NOLOAD first: reuse the copy the process already mapped (e.g. the one torch bundles)
+            lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD);
+            if (!lib) lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) { snprintf(a.why, sizeof a.why, "libnccl.so.2 not found (%s)", dlerror()); return a; }
+        a.GetUniqueId = (int (*)(NcclId *))dlsym(lib, "ncclGetUniqueId");
+        a.CommInitRank = (int (*)(nccl_comm_t *, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+        a.CommDestroy = (int (*)(nccl_comm_t))dlsym(lib, "ncclCommDestroy");
+        a.AllGather = (int (*)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t))dlsym(lib, "ncclAllGather");
+        a.GetErrorString = (const char *(*)(int))dlsym(lib, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.GetErrorString;
+        if (!a.ok) snprintf(a.why, sizeof a.why, "libnccl.so.2 lacks an expected symbol");
+        return a;
+    }();
+    return api;
+}
+#define NC(expr)                                                                                           \
+    do {                                                                                                   \
+        int r_ = (expr);                                                                                   \
+        if (r_ != 0) return fail(AM_ERR_CUDA, "%s: %s", #expr, nccl_api().GetErrorString(r_));             \
+    } while (0)
+}  // namespace
+
+struct am_comm {
+    nccl_comm_t comm = nullptr;
+    int nranks = 1, rank = 0, device = 0;
+    size_t record_peaks = 4096;       // peaks per rank in one all-gather record (grows if a rank ever overflows it)
+};
+
+am_status am_comm_get_unique_id(void *id_out) {
+    if (!id_out) return fail(AM_ERR_INVALID, "NULL argument");
+    NcclApi &api = nccl_api();
+    if (!api.ok) return fail(AM_ERR_UNSUPPORTED, "NCCL unavailable: %s", api.why);
+    NcclId id;
+    NC(api.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return AM_OK;
+}
+
+am_status am_comm_init(int nranks, int rank, const void *nccl_unique_id, am_comm **out) {
+    if (!out) return fail(AM_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (nranks < 1 || rank < 0 || rank >= nranks || !nccl_unique_id) return fail(AM_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+    NcclApi &api = nccl_api();
+    if (!api.ok) return fail(AM_ERR_UNSUPPORTED, "NCCL unavailable: %s", api.why);
+    am_comm *c = new (std::nothrow) am_comm();
+    if (!c) return fail(AM_ERR_NOMEM, "out of host memory");
+    c->nranks = nranks;
+    c->rank = rank;
+    cudaError_t e = cudaGetDevice(&c->device);
+    if (e != cudaSuccess) { delete c; return fail(AM_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e)); }
+    NcclId id;
+    memcpy(&id, nccl_unique_id, sizeof id);
+    int r = api.CommInitRank(&c->comm, nranks, id, rank);
+    if (r != 0) { delete c; return fail(AM_ERR_CUDA, "ncclCommInitRank: %s", api.GetErrorString(r)); }
+    *out = c;
+    return AM_OK;
+}
+void am_comm_destroy(am_comm *comm) {
+    if (!comm) return;
+    if (comm->comm) nccl_api().CommDestroy(comm->comm);
+    delete comm;
+}
+int am_comm_rank(const am_comm *comm) { return comm ? comm->rank : 0; }
+int am_comm_size(const am_comm *comm) { return comm ? comm->nranks : 1; }
+
+am_status am_calc_chunks_sharded(am_matcher *h, am_comm *comm, const void *stream, size_t buf_first_frame,
+                                 size_t buf_frames, size_t total_frames, am_sample_fmt fmt, am_mem mem, int scale,
+                                 size_t first_chunk, size_t num_chunks, am_peak *out, size_t cap, size_t *n_out) {
+    if (!h || !n_out) return fail(AM_ERR_INVALID, "NULL argument");
+    if (!comm || comm->nranks == 1)          // one rank: the shard is the stream
+        return am_calc_chunks_range(h, stream, buf_first_frame, buf_frames, total_frames, fmt, mem, scale, first_chunk,
+                                    num_chunks, 1, out, cap, n_out);
+    std::lock_guard<std::mutex> lk(h->mu);
+    *n_out = 0;
+    if (h->device != comm->device) return fail(AM_ERR_INVALID, "matcher lives on device %d, communicator on %d", h->device, comm->device);
+    NcclApi &api = nccl_api();
+    unsigned long long count = 0;
+    // A rank that fails locally still has to take part in the collective: it contributes count = ~0 and all ranks fail.
+    const am_status local = range_pass_device(h, stream, buf_first_frame, buf_frames, total_frames, fmt, mem, scale,
+                                              first_chunk, num_chunks, &count);
+    char local_err[sizeof g_err];
+    memcpy(local_err, g_err, sizeof g_err);
+    CU(cudaSetDevice(h->device));
+    const int R = comm->nranks;
+    std::vector<unsigned char> host;
+    std::vector<unsigned long long> counts((size_t)R);
+    for (int round = 0; round < 2; ++round) {
+        const size_t G = comm->record_peaks, rec = 16 + G * sizeof(am_peak);
+        TRY(h->d_gsend.reserve(rec));
+        TRY(h->d_grecv.reserve(rec * (size_t)R));
+        // record = [count u64][status u64][G peaks]; count and peaks come straight from the device buffers
+        unsigned long long head[2] = {local == AM_OK ? count : ~0ull, (unsigned long long)local};
+        CU(cudaMemcpyAsync(h->d_gsend.p, head, sizeof head, cudaMemcpyHostToDevice, h->stream));
+        const size_t n_here = local == AM_OK ? (size_t)std::min<unsigned long long>(count, G) : 0;
+        if (n_here) CU(cudaMemcpyAsync(h->d_gsend.p + 16, h->d_peaks.p, n_here * sizeof(am_peak), cudaMemcpyDeviceToDevice, h->stream));
+        NC(api.AllGather(h->d_gsend.p, h->d_grecv.p, rec, /* ncclChar */ 0, comm->comm, h->stream));
+        host.resize(rec * (size_t)R);
+        CU(cudaMemcpyAsync(host.data(), h->d_grecv.p, host.size(), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->stats.d2h_bytes += host.size();
+        unsigned long long worst = 0;
+        for (int r = 0; r < R; ++r) {
+            memcpy(&counts[(size_t)r], host.data() + rec * (size_t)r, 8);
+            if (counts[(size_t)r] == ~0ull) {
+                if (local != AM_OK) { memcpy(g_err, local_err, sizeof g_err); return local; }
+                return fail(AM_ERR_CUDA, "rank %d failed in its shard of the sharded calc_chunks", r);
+            }
+            worst = std::max(worst, counts[(size_t)r]);
+        }
+        if (worst <= G) break;                       // every rank's peaks fit the record
+        comm->record_peaks = (size_t)worst;          // all ranks see the same counts and grow alike; gather once more
+        if (round == 1) return fail(AM_ERR_CAPACITY, "peak records grew during the exchange");
+    }
+    const size_t rec = 16 + comm->record_peaks * sizeof(am_peak);
+    size_t total = 0;
+    for (int r = 0; r < R; ++r) total += (size_t)counts[(size_t)r];
+    std::vector<am_peak> all(total), kept(total);
+    size_t o = 0;
+    for (int r = 0; r < R; ++r) {
+        if (counts[(size_t)r]) memcpy(all.data() + o, host.data() + rec * (size_t)r + 16, (size_t)counts[(size_t)r] * sizeof(am_peak));
+        o += (size_t)counts[(size_t)r];
+    }
+    size_t nk = 0;
+    TRY(am_merge_peaks(all.data(), all.size(), h->sr, h->cfg.distance_s, kept.data(), kept.size(), &nk));
+    *n_out = nk;
+    if (nk > cap) return fail(AM_ERR_CAPACITY, "%zu peaks, capacity %zu", nk, cap);
+    if (nk) {
+        if (!out) return fail(AM_ERR_INVALID, "NULL output buffer");
+        memcpy(out, kept.data(), nk * sizeof(am_peak));
+    }
     return AM_OK;
 }
 

@@ -134,6 +134,116 @@ template <int R, bool INV> AM_HD void dft(float2 *v) {
     else dft32<INV>(v);
 }
 
+// ---- FMA-fused butterflies ---------------------------------------------------------------------
+// A twiddle multiply that feeds an add/sub pair costs 8 instructions when done separately (4 for the
+// product, 4 for the pair).  Folding the product into the sum (a + w b: 4 FMA) and taking the
+// difference as 2a - (a + w b) (2 FMA) makes it 6.  The radix-16 / radix-32 butterflies below apply
+// this to the inter-stage twiddles (first dft4 layer), to the constant W16 twiddles between the two
+// dft4 layers and to the radix-2 combine of the radix-32 butterfly: ~10 % fewer FP instructions per
+// transform.  AM_FFT_LEGACY keeps the unfused butterflies for A/B measurements.
+AM_HD float2 cfma(float2 a, float2 w, float2 b) {           // a + w b
+    return make_float2(fmaf(w.x, b.x, fmaf(-w.y, b.y, a.x)), fmaf(w.x, b.y, fmaf(w.y, b.x, a.y)));
+}
+AM_HD float2 cdbl_sub(float2 a, float2 s) { return make_float2(fmaf(2.0f, a.x, -s.x), fmaf(2.0f, a.y, -s.y)); }   // 2a - s
+template <bool INV> AM_HD float2 cw(float c, float s) { return make_float2(c, INV ? s : -s); }   // exp(-+ i phi), (c, s) = (cos, sin) phi
+// dft4 of (a0, w1 a1, w2 a2, w3 a3), natural order, in place: 24 instructions (28 unfused)
+template <bool INV> AM_HD void dft4_tw(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float2 w1, float2 w2, float2 w3) {
+    const float2 s0 = cfma(a0, w2, a2), d0 = cdbl_sub(a0, s0);
+    const float2 t1 = cmul(a1, w1);
+    const float2 s1 = cfma(t1, w3, a3), d1 = mul_mi<INV>(cdbl_sub(t1, s1));
+    a0 = cadd(s0, s1);
+    a1 = cadd(d0, d1);
+    a2 = csub(s0, s1);
+    a3 = csub(d0, d1);
+}
+// second dft4 layer of the 16-point butterfly with the constant twiddles W16^{n2 k1} folded in, then the
+// transposition to natural order
+template <bool INV> AM_HD void dft16_layer2(float2 *v) {
+    dft4<INV>(v[0], v[1], v[2], v[3]);
+    dft4_tw<INV>(v[4], v[5], v[6], v[7], cw<INV>(AM_C16_1, AM_S16_1), cw<INV>(AM_C8, AM_C8), cw<INV>(AM_S16_1, AM_C16_1));
+    {   // k1 = 2: twiddles W16^2, W16^4 = -+i, W16^6
+        const float2 m = mul_mi<INV>(v[10]);
+        const float2 s0 = cadd(v[8], m), d0 = csub(v[8], m);
+        const float2 t1 = cmul(v[9], cw<INV>(AM_C8, AM_C8));
+        const float2 s1 = cfma(t1, cw<INV>(-AM_C8, AM_C8), v[11]), d1 = mul_mi<INV>(cdbl_sub(t1, s1));
+        v[8] = cadd(s0, s1);
+        v[9] = cadd(d0, d1);
+        v[10] = csub(s0, s1);
+        v[11] = csub(d0, d1);
+    }
+    dft4_tw<INV>(v[12], v[13], v[14], v[15], cw<INV>(AM_S16_1, AM_C16_1), cw<INV>(-AM_C8, AM_C8), cw<INV>(-AM_C16_1, -AM_S16_1));
+    float2 t;
+#define AM_SWAP(a, b) t = v[a]; v[a] = v[b]; v[b] = t;
+    AM_SWAP(1, 4) AM_SWAP(2, 8) AM_SWAP(3, 12) AM_SWAP(6, 9) AM_SWAP(7, 13) AM_SWAP(11, 14)
+#undef AM_SWAP
+}
+// NBF 16-point butterflies (v[16 f + r]) whose inputs carry the same geometric twiddles:
+//   TW = 0: none;  TW = 1: v[r] *= u^r;  TW = 2: v[r] *= b u^r.
+// The twiddles of one first-layer group (r = n2 + 4 n1) are generated right before they are used
+// (t0 = b u^n2, t0 u^4, t0 u^8, t0 u^12), so few of them are live at a time.
+template <bool INV, int TW, int NBF> AM_HD void dft16_f(float2 *v, float2 b, float2 u) {
+    if constexpr (TW == 0) {
+#pragma unroll
+        for (int f = 0; f < NBF; ++f) {
+            float2 *x = v + 16 * f;
+            dft4<INV>(x[0], x[4], x[8], x[12]);
+            dft4<INV>(x[1], x[5], x[9], x[13]);
+            dft4<INV>(x[2], x[6], x[10], x[14]);
+            dft4<INV>(x[3], x[7], x[11], x[15]);
+        }
+    } else {
+        const float2 u2 = cmul(u, u), u3 = cmul(u2, u), u4 = cmul(u2, u2), u8 = cmul(u4, u4), u12 = cmul(u8, u4);
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+            float2 t0 = n2 == 0 ? make_float2(1.f, 0.f) : (n2 == 1 ? u : (n2 == 2 ? u2 : u3));
+            if constexpr (TW == 2) t0 = n2 == 0 ? b : cmul(b, t0);
+            const bool unit = (TW == 1 && n2 == 0);
+            const float2 t1 = unit ? u4 : cmul(t0, u4), t2 = unit ? u8 : cmul(t0, u8), t3 = unit ? u12 : cmul(t0, u12);
+#pragma unroll
+            for (int f = 0; f < NBF; ++f) {
+                float2 *x = v + 16 * f;
+                if (!unit) x[n2] = cmul(x[n2], t0);
+                dft4_tw<INV>(x[n2], x[4 + n2], x[8 + n2], x[12 + n2], t1, t2, t3);
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < NBF; ++f) dft16_layer2<INV>(v + 16 * f);
+}
+// 32-point butterfly, optionally with input twiddles v[r] *= w^r (TW)
+template <bool INV, bool TW> AM_HD void dft32_f(float2 *v, float2 w) {
+    float2 e[16], o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    if constexpr (TW) {
+        const float2 u = cmul(w, w);
+        dft16_f<INV, 1, 1>(e, u, u);
+        dft16_f<INV, 2, 1>(o, w, u);
+    } else {
+        dft16_f<INV, 0, 1>(e, w, w);
+        dft16_f<INV, 0, 1>(o, w, w);
+    }
+    constexpr float C[16] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                             0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f,
+                             0.f, -0.19509032201612826785f, -0.38268343236508977173f, -0.55557023301960222474f,
+                             -0.70710678118654752440f, -0.83146961230254523708f, -0.92387953251128675613f, -0.98078528040323044913f};
+    constexpr float S[16] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                             0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f, 0.98078528040323044913f,
+                             1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                             0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f, 0.19509032201612826785f};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (k == 0 || k == 8) {
+            const float2 t = k == 0 ? o[0] : mul_mi<INV>(o[8]);
+            v[k] = cadd(e[k], t);
+            v[k + 16] = csub(e[k], t);
+        } else {
+            v[k] = cfma(e[k], cw<INV>(C[k], S[k]), o[k]);
+            v[k + 16] = cdbl_sub(e[k], v[k]);
+        }
+    }
+}
+
 // v[r] *= w^r, r = 1..R-1, with w^r built by a depth-log2(R) product tree
 template <int R> AM_HD void apply_twiddle_powers(float2 *v, float2 w1) {
     v[1] = cmul(v[1], w1);
@@ -210,18 +320,68 @@ template <int LOG2N, int LOG2B, bool INV, int E = EPT> struct RegFFT {
         idx = (id >> LOG2B) + s * (N >> RB);
     }
 
+    // twiddle W_{Ns R}^k of butterfly l of stage ST (conjugated for the inverse)
+    template <int ST> static AM_HD float2 stage_twiddle(int gtid, int l, const float2 *__restrict__ tw) {
+        constexpr int RB = bits_at(ST), LOGNS = logns_at(ST);
+        const int q = (gtid + l * GT) >> LOG2B;
+        const int k = q & ((1 << LOGNS) - 1);
+        float2 w = tw[k << (TW_LOG2 - LOGNS - RB)];
+        if (INV) w.y = -w.y;
+        return w;
+    }
     // twiddle + butterflies of stage ST on the registers
     template <int ST> static AM_HD void butterfly(float2 (&v)[EPT], int gtid, const float2 *__restrict__ tw) {
         constexpr int RB = bits_at(ST), R = 1 << RB, NB = EPT / R, LOGNS = logns_at(ST);
+#ifndef AM_FFT_LEGACY
+        if constexpr (R == 16 || R == 32) {
+            if constexpr (ST == 0) {
+                if constexpr (R == 16) dft16_f<INV, 0, NB>(v, make_float2(1.f, 0.f), make_float2(1.f, 0.f));
+                else {
+#pragma unroll
+                    for (int l = 0; l < NB; ++l) dft32_f<INV, false>(&v[l * R], make_float2(1.f, 0.f));
+                }
+            } else if constexpr (R == 16 && NB > 1 && ((GT >> LOG2B) % (1 << LOGNS)) == 0) {
+                // every butterfly of the thread has the same k: one set of twiddle powers serves all of them
+                const float2 w = stage_twiddle<ST>(gtid, 0, tw);
+                dft16_f<INV, 1, NB>(v, w, w);
+            } else {
+#pragma unroll
+                for (int l = 0; l < NB; ++l) {
+                    const float2 w = stage_twiddle<ST>(gtid, l, tw);
+                    if constexpr (R == 16) dft16_f<INV, 1, 1>(&v[l * R], w, w);
+                    else dft32_f<INV, true>(&v[l * R], w);
+                }
+            }
+            return;
+        }
+#endif
 #pragma unroll
         for (int l = 0; l < NB; ++l) {
-            if constexpr (ST > 0) {
-                int q = (gtid + l * GT) >> LOG2B;
-                int k = q & ((1 << LOGNS) - 1);
-                float2 w = tw[k << (TW_LOG2 - LOGNS - RB)];          // W_{Ns R}^k
-                if (INV) w.y = -w.y;
-                apply_twiddle_powers<R>(&v[l * R], w);
+            if constexpr (ST > 0) apply_twiddle_powers<R>(&v[l * R], stage_twiddle<ST>(gtid, l, tw));
+            dft<R, INV>(&v[l * R]);
+        }
+    }
+    // Stage 0 with geometric input twiddles v[l R + r] *= base[l] step^r (the four-step twiddles of the inverse
+    // column pass ride on the first butterflies)
+    static AM_HD void butterfly0_geo(float2 (&v)[EPT], const float2 *base, float2 step) {
+        constexpr int RB = bits_at(0), R = 1 << RB, NB = EPT / R;
+#pragma unroll
+        for (int l = 0; l < NB; ++l) {
+#ifndef AM_FFT_LEGACY
+            if constexpr (R == 16) { dft16_f<INV, 2, 1>(&v[l * R], base[l], step); continue; }
+#endif
+            float2 w[R];
+            w[0] = base[l];
+            if (R >= 2) w[1] = cmul(base[l], step);
+            float2 sp = step;
+#pragma unroll
+            for (int h = 2; h < R; h <<= 1) {
+                sp = cmul(sp, sp);
+#pragma unroll
+                for (int i = 0; i < h; ++i) w[h + i] = cmul(w[i], sp);
             }
+#pragma unroll
+            for (int i = 0; i < R; ++i) v[l * R + i] = cmul(v[l * R + i], w[i]);
             dft<R, INV>(&v[l * R]);
         }
     }
@@ -279,9 +439,10 @@ template <int LOG2N, int LOG2B, bool INV, int E = EPT> struct RegFFT {
     // __syncthreads() before the buffer is written again.
     // LEAD_SYNC = true puts a barrier in front of the first exchange write (after the first butterflies) for a
     // caller whose threads may still be reading the buffer when they enter.
-    template <int ST = 0, bool TAIL_SYNC = true, bool LEAD_SYNC = false>
+    // SKIP_B0 = true: the caller has already done stage 0's butterflies (butterfly0_geo).
+    template <int ST = 0, bool TAIL_SYNC = true, bool LEAD_SYNC = false, bool SKIP_B0 = false>
     static __device__ __forceinline__ void run(float2 (&v)[EPT], float2 *sm, int gtid, const float2 *__restrict__ tw) {
-        butterfly<ST>(v, gtid, tw);
+        if constexpr (!(ST == 0 && SKIP_B0)) butterfly<ST>(v, gtid, tw);
         AM_TL(8 + (INV ? 9 : 0) + ST * 3);
         if constexpr (ST + 1 < NST) {
             if constexpr (ST == 0 && LEAD_SYNC) __syncthreads();
@@ -291,7 +452,7 @@ template <int LOG2N, int LOG2B, bool INV, int E = EPT> struct RegFFT {
             xchg_read<ST + 1>(v, sm, gtid);
             if constexpr (TAIL_SYNC || ST + 2 < NST) __syncthreads();
             AM_TL(8 + (INV ? 9 : 0) + ST * 3 + 2);
-            run<ST + 1, TAIL_SYNC, LEAD_SYNC>(v, sm, gtid, tw);
+            run<ST + 1, TAIL_SYNC, LEAD_SYNC, SKIP_B0>(v, sm, gtid, tw);
         }
     }
     // Same, calling hook() once when the exchange buffer has been read for the last time (before the last stage's

@@ -22,6 +22,7 @@
 // maths of MyConvolve::correlate (:414-457).
 #pragma once
 #include "am_fft.cuh"
+#include "am_peaks.cuh"
 
 namespace amk {
 
@@ -84,9 +85,9 @@ struct BlockGroup {
     long long c_g0;
     float scalar;       // 1/N or 1/(N sum s^2)
     // Summary mode (k_col_inv with 16-column tiles only): for every aligned run of 16 outputs the kernel writes
-    // rsum[(g - c_g0) >> 4] = {min, max, first, last} and stores the 16 values themselves only when max >= theta.
-    // theta = -inf keeps the correlation dense.  nullptr: no records, plain dense stores.
-    float4 *rsum;
+    // rsum.mm[(g - c_g0) >> 4] = {min, max}, rsum.fl[...] = {first, last} and stores the 16 values themselves only
+    // when max >= theta.  theta = -inf keeps the correlation dense.  mm == nullptr: no records, plain dense stores.
+    amp::RunRecs rsum;
     float theta;
 };
 
@@ -198,6 +199,21 @@ template <int R> __device__ __forceinline__ void twiddle_geo(float2 *v, float2 b
     for (int i = 0; i < R; ++i) v[i] = cmul(v[i], w[i]);
 }
 
+// Four-step twiddles of one thread: column n2, rows k1 = q0 + l dq + s NB dq (l < NB butterflies, s < R), i.e.
+// W_N^{n2 k1} = base[l] step^s with base[l] = W^{n2 q0} z^l, step = z^NB, z = W^{n2 dq}: two sincospif per thread,
+// the rest are products.
+template <int NB> __device__ __forceinline__ void fourstep_bases(float2 (&base)[NB], float2 &step, unsigned n2, unsigned q0,
+                                                                unsigned dq, float two_over_n, bool inverse) {
+    using amfft::cmul;
+    base[0] = twiddle_big(n2 * q0, two_over_n, inverse);
+    const float2 z = twiddle_big(n2 * dq, two_over_n, inverse);
+    step = z;
+#pragma unroll
+    for (int l = 1; l < NB; ++l) base[l] = cmul(base[l - 1], z);
+#pragma unroll
+    for (int h = 1; h < NB; h <<= 1) step = cmul(step, step);
+}
+
 template <int FMT, class F, int LT>
 __device__ __forceinline__ void load_tile_fast(float2 (&v)[F::EPT], const BlockGroup &g, long long v0, int log2n2, int n2_0, int tid) {
     const long long f0 = v0 - g.sv.lead - g.sv.buf_first;
@@ -260,10 +276,11 @@ __device__ __forceinline__ void col_fwd_finish(float2 (&v)[E], float2 *sm_all, i
     constexpr int RB = F::bits_at(F::NST - 1), R = 1 << RB, NB = E / R;
     const int t = tid & ((1 << LT) - 1), q = tid >> LT;      // q < N1 / E
     const unsigned n2 = n2_0 + t;
+    static_assert((F::GT >> LT) * NB == ((1 << L1) >> RB), "k1 = q + l N1/E + s N1/R");
+    float2 base[NB], step;                                    // k1 = q_l + s (N1 / R): W_N^{n2 k1} = W_N^{n2 q_l} (W_N^{n2 N1 / R})^s
+    fourstep_bases<NB>(base, step, n2, (unsigned)q, (unsigned)(F::GT >> LT), two_over_n, false);
 #pragma unroll
-    for (int l = 0; l < NB; ++l)       // k1 = q_l + s (N1 / R): W_N^{n2 k1} = W_N^{n2 q_l} (W_N^{n2 N1 / R})^s
-        twiddle_geo<R>(&v[l * R], twiddle_big(n2 * (unsigned)(q + l * (F::GT >> LT)), two_over_n, false),
-                       twiddle_big(n2 << (L1 - RB), two_over_n, false));
+    for (int l = 0; l < NB; ++l) twiddle_geo<R>(&v[l * R], base[l], step);
     AM_TL(3);
 #pragma unroll
     for (int l = 0; l < NB; ++l)
@@ -465,22 +482,28 @@ k_col_inv(BlockGroup g, int log2n2_arg, const float2 *__restrict__ A, const floa
     const float2 *Ap = A + ((size_t)pair << (L1 + log2n2));
     float2 v[EPT];
     constexpr int RB = I::bits_at(0), R = 1 << RB, NB = EPT / R;
+    // conjugate four-step twiddles W_N^{-n2 k1}, k1 = q_l + r N1 / R: per butterfly a geometric sequence base_l step^r
+    // that rides on the first butterflies (butterfly0_geo); the column n2 = n2_0 + t is the same for every l
+    static_assert(I::GT % Cfg::T == 0, "tile columns divide the thread count");
+    static_assert((I::GT >> Cfg::LT) * NB == ((1 << L1) >> RB), "k1 = q + l N1/E + r N1/R");
+    float2 base[NB], step;
+    const unsigned n2 = n2_0 + (tid & (Cfg::T - 1));
 #pragma unroll
     for (int l = 0; l < NB; ++l) {
-        const int id = tid + l * I::GT;
-        const int t = id & (Cfg::T - 1), q = id >> Cfg::LT;
-        const unsigned n2 = n2_0 + t;
+        const int q = (tid + l * I::GT) >> Cfg::LT;
 #pragma unroll
         for (int r = 0; r < R; ++r) v[l * R + r] = Ap[((size_t)(q + r * ((1 << L1) >> RB)) << log2n2) + n2];
-        float2 base = twiddle_big(n2 * (unsigned)q, two_over_n, true);
-        base.x *= g.scalar;                                         // the output scale rides on the twiddles
-        base.y *= g.scalar;
-        twiddle_geo<R>(&v[l * R], base, twiddle_big(n2 << (L1 - RB), two_over_n, true));
     }
-    I::run(v, sm_all, tid, tw);
+    fourstep_bases<NB>(base, step, n2, (unsigned)(tid >> Cfg::LT), (unsigned)(I::GT >> Cfg::LT), two_over_n, true);
+    base[0].x *= g.scalar;                                          // the output scale rides on the twiddles
+    base[0].y *= g.scalar;
+#pragma unroll
+    for (int l = 1; l < NB; ++l) { base[l].x *= g.scalar; base[l].y *= g.scalar; }
+    I::butterfly0_geo(v, base, step);
+    I::template run<0, true, false, true>(v, sm_all, tid, tw);
     const long long o0 = g.g0 + (long long)(2 * pair) * g.VN;
     if constexpr (Cfg::LT == 4) {
-        if (g.rsum != nullptr) {
+        if (g.rsum.mm != nullptr) {
             // Summary epilogue: transpose the tile through the (now idle) exchange buffer so that every thread owns
             // whole rows = aligned runs of 16 outputs of both blocks, then write one {min, max, first, last} record
             // per run and the run itself (four 128-bit stores) only if its maximum reaches theta.
@@ -524,7 +547,8 @@ k_col_inv(BlockGroup g, int log2n2_arg, const float2 *__restrict__ A, const floa
                             if (i < valid) { mn = fminf(mn, vals[i]); mx = fmaxf(mx, vals[i]); last = vals[i]; }
                     }
                     const long long ci = o - g.c_g0;
-                    g.rsum[ci >> 4] = make_float4(mn, mx, vals[0], last);
+                    g.rsum.mm[ci >> 4] = make_float2(mn, mx);
+                    g.rsum.fl[ci >> 4] = make_float2(vals[0], last);
                     if (mx >= g.theta) {
                         float *dst = g.c + ci;
                         if (valid == 16) {

@@ -103,23 +103,34 @@ k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin
 // Any other geometry sets FLAG_NEED_DENSE and the host repeats the call with the dense correlation.
 constexpr unsigned FLAG_OVERFLOW = 1u, FLAG_NEED_DENSE = 2u;
 
+// The records live in two arrays so that the tile pass (which only needs min / max) reads 8 bytes per run:
+//   mm[r] = {min, max},  fl[r] = {first, last}   of the run of outputs [16 r, 16 r + 16) of the segment buffer
+struct RunRecs {
+    float2 *mm, *fl;
+    __host__ __device__ RunRecs offset(long long runs) const { return RunRecs{mm + runs, fl + runs}; }
+};
+
 struct RunView {
-    const float4 *rs;       // records of this chunk, rs[0] = run of the chunk's first output
+    const float2 *mm, *fl;  // records of this chunk, [0] = run of the chunk's first output
     long long nr_full;      // full runs
     int pv;                 // valid outputs of run nr_full (0: there is no partial run)
     bool masked;            // the partial run's record covers only the valid outputs
     __device__ __forceinline__ long long total() const { return nr_full + (pv ? 1 : 0); }
     __device__ __forceinline__ int count(long long r) const { return r == nr_full ? pv : 16; }
     __device__ __forceinline__ void minmax(long long r, float &mn, float &mx) const {
-        const float4 q = __ldg(rs + r);
-        if (r == nr_full && !masked) { mn = q.z; mx = q.z; } else { mn = q.x; mx = q.y; }
+        if (r == nr_full && !masked) { mn = mx = __ldg(fl + r).x; return; }
+        const float2 q = __ldg(mm + r);
+        mn = q.x; mx = q.y;
     }
+    __device__ __forceinline__ float first(long long r) const { return __ldg(fl + r).x; }
+    __device__ __forceinline__ float last(long long r) const { return __ldg(fl + r).y; }
 };
-__device__ __forceinline__ RunView make_run_view(const float4 *rsum, const ChunkGeom &g, long long chunk, long long V,
+__device__ __forceinline__ RunView make_run_view(const RunRecs &rsum, const ChunkGeom &g, long long chunk, long long V,
                                                  unsigned snippet) {
     RunView rv;
     const long long cs = g.C * chunk - g.c_g0;
-    rv.rs = rsum + ((snippet * g.c_stride + cs) >> 4);
+    rv.mm = rsum.mm + ((snippet * g.c_stride + cs) >> 4);
+    rv.fl = rsum.fl + ((snippet * g.c_stride + cs) >> 4);
     rv.nr_full = V >> 4;
     rv.pv = (int)(V & 15);
     rv.masked = (cs + V == g.seg_end);
@@ -128,7 +139,7 @@ __device__ __forceinline__ RunView make_run_view(const float4 *rsum, const Chunk
 
 // grid (ceil(tiles_stride / 8), chunks in segment, snippets), 256 threads: one tile (64 runs) per warp
 __global__ void __launch_bounds__(256)
-k_tile_from_runs(const float4 *__restrict__ rsum, ChunkGeom g, float *__restrict__ tmin, float *__restrict__ tmax,
+k_tile_from_runs(RunRecs rsum, ChunkGeom g, float *__restrict__ tmin, float *__restrict__ tmax,
                  unsigned *flags) {
     const long long chunk = g.first_chunk + blockIdx.y;
     const long long V = chunk_valid_len(g, chunk);
@@ -346,7 +357,7 @@ struct PeakOut {
 // SUM: summary mode -- `rsum` holds the run records, only runs with max >= theta are present in c.
 template <bool SUM>
 __global__ void __launch_bounds__(256)
-k_chunk_peaks(const float *__restrict__ c, const float4 *__restrict__ rsum, float theta, ChunkGeom g,
+k_chunk_peaks(const float *__restrict__ c, RunRecs rsum, float theta, ChunkGeom g,
               const float *__restrict__ tmin_all, const float *__restrict__ tmax_all, float min_prom,
               unsigned long long min_dist, int pk_cap, int sm_tiles, PeakOut out) {
     extern __shared__ unsigned char smraw[];
@@ -411,7 +422,7 @@ k_chunk_peaks(const float *__restrict__ c, const float4 *__restrict__ rsum, floa
         long long k0 = t << TP_LOG2;
         if constexpr (SUM) {
             // qualifying runs of the tile (two per lane); a lane scans its run serially -- such runs are rare
-            auto val = [&](long long a) { return (a & 15) == 0 ? __ldg(rv.rs + (a >> 4)).z : __ldg(y + a); };
+            auto val = [&](long long a) { return (a & 15) == 0 ? rv.first(a >> 4) : __ldg(y + a); };
             for (int i = 0; i < 2; ++i) {
                 const long long r = (t << 6) + i * 32 + lane;
                 if (r >= rv.total()) continue;
@@ -423,7 +434,7 @@ k_chunk_peaks(const float *__restrict__ c, const float4 *__restrict__ rsum, floa
                     const long long k = (r << 4) + sidx;
                     if (k < 1 || k >= V - 1) continue;
                     const float yk = __ldg(y + k);
-                    const float prev = sidx ? __ldg(y + k - 1) : __ldg(rv.rs + r - 1).w;
+                    const float prev = sidx ? __ldg(y + k - 1) : rv.last(r - 1);
                     if (!(prev < yk) || !(yk - cmin >= min_prom)) continue;
                     long long a = k + 1;
                     while (a < V - 1 && val(a) == yk) ++a;          // plateau (its runs have max >= yk >= theta)
@@ -481,8 +492,8 @@ k_chunk_peaks(const float *__restrict__ c, const float4 *__restrict__ rsum, floa
             float prom = h - fmaxf(lmin, rmin);
             p_prom[i] = prom;
             if constexpr (SUM) {
-                p_ld[i] = h - ((s & 15) ? __ldg(y + s - 1) : __ldg(rv.rs + (s >> 4) - 1).w);
-                p_rd[i] = h - ((e & 15) ? __ldg(y + e) : __ldg(rv.rs + (e >> 4)).z);
+                p_ld[i] = h - ((s & 15) ? __ldg(y + s - 1) : rv.last((s >> 4) - 1));
+                p_rd[i] = h - ((e & 15) ? __ldg(y + e) : rv.first(e >> 4));
             } else {
                 p_ld[i] = h - __ldg(y + s - 1);
                 p_rd[i] = h - __ldg(y + e);
@@ -558,7 +569,7 @@ k_chunk_peaks(const float *__restrict__ c, const float4 *__restrict__ rsum, floa
 // Test hook: build the run records the summary epilogue of k_col_inv would have written for a correlation that is
 // already in memory, and poison (NaN) every run it would not have stored, so that any read the summary-mode
 // kernels are not entitled to shows up as a wrong result.
-__global__ void k_debug_make_runs(float *__restrict__ c, long long n, float theta, float4 *__restrict__ rsum) {
+__global__ void k_debug_make_runs(float *__restrict__ c, long long n, float theta, RunRecs rsum) {
     const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if ((r << 4) >= n) return;
     const long long left = n - (r << 4);
@@ -566,7 +577,8 @@ __global__ void k_debug_make_runs(float *__restrict__ c, long long n, float thet
     float *p = c + (r << 4);
     float mn = p[0], mx = p[0], last = p[0];
     for (int i = 1; i < valid; ++i) { mn = fminf(mn, p[i]); mx = fmaxf(mx, p[i]); last = p[i]; }
-    rsum[r] = make_float4(mn, mx, p[0], last);
+    rsum.mm[r] = make_float2(mn, mx);
+    rsum.fl[r] = make_float2(p[0], last);
     if (!(mx >= theta))
         for (int i = 0; i < valid; ++i) p[i] = __int_as_float(0x7fc00000);
 }

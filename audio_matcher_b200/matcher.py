@@ -9,6 +9,7 @@ All numeric work happens in libaudio_matcher_b200.so; nothing here computes a co
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass, field
 from enum import IntEnum
 from typing import Iterable, Sequence
@@ -211,9 +212,42 @@ class CudaConvolve:
         """CorrelateAlgo::scale (audio_matcher.rs:73-75): in-place multiply by the inverse autocorrelation."""
         data *= np.float32(self.inverse_sample_auto_correlation())
 
+    def set_progress(self, fn) -> None:
+        """fn(phase, first_chunk, n_chunks) or None: the progress callbacks of audio_matcher.rs:102-117,129
+        (phase 0: a segment of logical chunks was submitted to the GPU; phase 1: the call's peaks are final)."""
+        self._progress = None if fn is None else N.PROGRESS_FN(lambda user, phase, c0, nc: fn(phase, c0, nc))
+        N.check(N.lib().am_matcher_set_progress(self._h, C.cast(self._progress, C.c_void_p) if self._progress else None, None))
+
     # --- calc_chunks plumbing ---------------------------------------------------------------
     def num_chunks(self, frames: int) -> int:
         return N.lib().am_num_chunks(self._h, frames)
+
+    def chunk_geometry(self) -> tuple[int, int]:
+        """(chunk, overlap) in samples as calc_chunks rounds them (audio_matcher.rs:99-100)."""
+        c, ov = C.c_size_t(), C.c_size_t()
+        N.check(N.lib().am_chunk_geometry(self._h, C.byref(c), C.byref(ov)))
+        return c.value, ov.value
+
+    def shard_frames(self, first_chunk: int, num_chunks: int, total_frames: int) -> tuple[int, int]:
+        """Frames [lo, hi) a rank must hold for logical chunks [first_chunk, first_chunk + num_chunks): the library's
+        own geometry, one source of truth for shard buffers."""
+        lo, hi = C.c_size_t(), C.c_size_t()
+        N.check(N.lib().am_shard_frames(self._h, total_frames, first_chunk, num_chunks, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def calc_chunks_sharded(self, shard_samples, scale: bool, *, total_frames: int, buf_first_frame: int,
+                            first_chunk: int, num_chunks: int, comm: "Comm | None" = None, cap: int = 1 << 16) -> list[Peak]:
+        """am_calc_chunks_sharded: this rank's chunk range, one ncclAllGather of the device-resident peak records
+        inside the library, global sort + neighbour filter; every rank returns the complete list."""
+        comm = comm or Comm.current
+        if comm is None:
+            raise RuntimeError("no communicator: call comm_init_from_torch() / Comm(...) first")
+        ptr, frames, fmt, mem, keep = _describe(shard_samples)
+        buf = (N.AmPeak * cap)()
+        got = C.c_size_t()
+        N.check(N.lib().am_calc_chunks_sharded(self._h, comm._c, ptr, buf_first_frame, frames, int(total_frames), fmt, mem,
+                                               int(bool(scale)), first_chunk, int(num_chunks), buf, cap, C.byref(got)))
+        return [Peak._from_native(buf[i]) for i in range(got.value)]
 
     def _calc(self, samples, scale: bool, total_frames: int | None, buf_first_frame: int, first_chunk: int,
               num_chunks: int | None, final_filter: bool, cap: int) -> list[Peak]:
@@ -271,11 +305,56 @@ def shard_chunks(total_chunks: int, world_size: int, rank: int) -> tuple[int, in
 
 def shard_frames(first_chunk: int, num_chunks: int, total_frames: int, sr: int, config: Config, m: int) -> tuple[int, int]:
     """Frames [lo, hi) a rank must hold for its chunk range: its chunks plus the overlap halo."""
-    C_ = int(round(config.chunk_size * sr))
-    ov = int(round((config.overlap_length if config.overlap_length >= 0 else m / sr) * sr))
+    # f64::round / llround: half away from zero (Python's round() is half to even); CudaConvolve.shard_frames asks
+    # the library itself and is what callers with a handle should use
+    C_ = int(math.floor(config.chunk_size * sr + 0.5))
+    ov = int(math.floor((config.overlap_length if config.overlap_length >= 0 else m / sr) * sr + 0.5))
     lo = C_ * first_chunk
     hi = min(total_frames, C_ * (first_chunk + num_chunks - 1) + C_ + ov) if num_chunks > 0 else lo
     return lo, hi
+
+
+class Comm:
+    """am_comm: the NCCL communicator of the C ABI (one process per GPU).  `unique_id` is the 128-byte id rank 0
+    got from Comm.unique_id(); how it reaches the other ranks is the caller's business."""
+
+    current: "Comm | None" = None
+
+    def __init__(self, nranks: int, rank: int, unique_id: bytes):
+        if len(unique_id) != N.COMM_ID_BYTES:
+            raise ValueError("unique_id must be 128 bytes")
+        c = C.c_void_p()
+        idbuf = C.create_string_buffer(bytes(unique_id), N.COMM_ID_BYTES)
+        N.check(N.lib().am_comm_init(nranks, rank, idbuf, C.byref(c)))
+        self._c, self.nranks, self.rank = c, nranks, rank
+        Comm.current = self
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(N.COMM_ID_BYTES)
+        N.check(N.lib().am_comm_get_unique_id(buf))
+        return buf.raw
+
+    def close(self) -> None:
+        if getattr(self, "_c", None):
+            N.lib().am_comm_destroy(self._c)
+            self._c = None
+            if Comm.current is self:
+                Comm.current = None
+
+
+def comm_init_from_torch(group=None) -> Comm:
+    """Bootstrap the C-ABI communicator from an initialised torch.distributed group: rank 0's unique id is broadcast
+    as 128 bytes (torch is only the messenger; the data path collective is the library's own ncclAllGather)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.zeros(N.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(Comm.unique_id()), dtype=torch.uint8).to(dev)
+    dist.broadcast(t, src=0, group=group)
+    return Comm(world, rank, bytes(t.cpu().numpy().tobytes()))
 
 
 def _pack(peaks: Sequence[Peak]):
@@ -340,6 +419,10 @@ def calc_chunks_sharded(sr: int, shard_samples, algo_with_sample: CudaConvolve, 
     are all-gathered, and every rank applies the global sort + neighbour filter."""
     if set_config:
         algo_with_sample.set_config(config)
+    if Comm.current is not None and group is None:
+        return algo_with_sample.calc_chunks_sharded(shard_samples, scale, total_frames=total_frames, buf_first_frame=buf_first_frame,
+                                                    first_chunk=first_chunk, num_chunks=num_chunks, cap=cap)
+    # no C-ABI communicator (CPU tests over gloo): gather the records through torch.distributed
     arr, n = algo_with_sample._calc_raw(shard_samples, scale, total_frames, buf_first_frame, first_chunk, num_chunks,
                                         False, cap)
     arr, n = gather_raw(arr, n, group)

@@ -4,16 +4,19 @@
   python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
   python bench.py --impl reference --gpus N ...            the reference algorithm's CPU path (oracle port)
 
-A step is one calc_chunks pass over the whole workload (default: BASELINE.json configs[1], one 10 s
-snippet vs a 24 h 48 kHz mono int16 stream per GPU, overlap-save block 2^22).  With N > 1 every rank
-matches its own 24 h shard of an N*24 h stream (weak scaling; chunk ranges + halo, no data-path
-collective) and only the peak candidates are all-gathered over NCCL.  `value` is timed with CUDA events
-with the PCM already in HBM; `e2e` is the same call with the PCM in pinned host memory (H2D inside the
-timed region) and the peak list read back.  One JSON line on stdout from rank 0.
+A step is one calc_chunks pass over the whole workload (headline: BASELINE.json configs[1], one 10 s snippet vs a
+24 h 48 kHz mono int16 stream per GPU, overlap-save block 2^22).  With N > 1 every rank matches its own 24 h shard
+of an N*24 h stream (weak scaling; chunk ranges + halo, no data-path collective) and only the peak candidates are
+all-gathered over NCCL, inside the C ABI (am_calc_chunks_sharded).  `value` is timed with CUDA events with the PCM
+already in HBM; `e2e` is the same call with the PCM in pinned host memory (H2D inside the timed region) and the peak
+list read back; `e2e.variants` adds what a Vec<i16> / Vec<f32> caller gets (pageable memory).  The other BASELINE
+configs (cfg 1 with its --distance sweep, cfg 3, cfg 4, cfg 5) are measured in the same run and reported in
+`other_configs`.  One JSON line on stdout from rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -35,15 +38,24 @@ WORKLOADS = {
 METRIC = "audio-hours matched/sec (snippet vs stream)"
 UNIT = "audio-hours/s"
 CHUNK_S, DIST_S, PROM = 60.0, 480.0, 0.13
-# dram__bytes_read.sum + dram__bytes_write.sum per block pair at N = 2^22, from the ncu --set full capture
-# summarised in profiles/r01_ncu_full_streaming.csv (64-pair launches: k_row32 2.181 + 2.090 GB, k_col_fwd_stream
-# 0.959 + 2.092 GB, k_col_inv 2.148 + 0.460 GB in summary mode)
-NCU_DRAM_BYTES_PER_PAIR_2P22 = {"k_row": 66.7e6, "k_col_fwd": 47.7e6, "k_col_inv": 40.8e6}
 PLANT_PERIOD_S, PLANT_JITTER_S = 600.0, 30.0
+# dram__bytes_read.sum + dram__bytes_write.sum per block pair at N = 2^22 from one `ncu --set full` capture of a
+# 64-pair launch group, keyed by the hash of the kernel sources the capture was taken with: a stale table reports
+# traffic = null instead of a wrong number.  (profiles/r02_ncu_full.csv)
+NCU_TRAFFIC = {"kernel_src_sha16": "", "file": "profiles/r02_ncu_full.csv",
+               "bytes_per_pair": {"k_row": 66.7e6, "k_col_fwd": 47.7e6, "k_col_inv": 40.8e6}}
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def kernel_src_sha16() -> str:
+    h = hashlib.sha256()
+    for f in ("am_fft.cuh", "am_kernels.cuh", "am_peaks.cuh"):
+        with open(os.path.join(ROOT, "audio_matcher_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def measured_hbm_peak():
@@ -52,6 +64,15 @@ def measured_hbm_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_cores() -> int:
+    """Threads the CPU arm may use: the CPUs this process is allowed on.  OMP_NUM_THREADS is deliberately ignored
+    (torchrun exports OMP_NUM_THREADS=1, which is not a statement about the host)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class ClockSampler:
@@ -132,47 +153,215 @@ def plant_plan(sr, snippet_s, total_frames):
     return out
 
 
-def run_reference(args, wl, out_stream):
-    """The reference algorithm's own CPU path (exact-length complex FFTs per 60 s chunk, snippet FFT
-    recomputed per chunk, one worker thread per core), via the oracle port -- the Rust crate cannot be
-    built in this image.  Each step is a bounded sample of the workload."""
+def workload_name(name, wl):
+    sr, ch, snip_s, hours, fft_log2, n_snip = wl
+    return (f"{name}: {'one' if n_snip == 1 else n_snip} {snip_s:g} s snippet{'s' if n_snip > 1 else ''} vs {hours:g} h {sr} Hz {'stereo' if ch == 2 else 'mono'} int16 "
+            f"stream per GPU, chunk 60 s, distance 480 s, prominence 0.13")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm's own CPU path through the oracle port (the Rust crate cannot be built
+# in this image: no cargo/rustc, four private git dependencies).
+# ---------------------------------------------------------------------------------------------------------
+def cpu_sample(wl, chunks, cores, precision=32, distance_s=DIST_S):
+    """One pass of the oracle over `chunks` logical chunks of the workload with `cores` threads -> (seconds, peaks)."""
+    from oracle import am_oracle as orc
+    sr, ch, snip_s, hours, fft_log2, n_snip = wl
+    if not hasattr(cpu_sample, "_cache") or cpu_sample._cache[0] != (wl, chunks):
+        pcm, snip, _ = orc.synth_case(sr, chunks * CHUNK_S + snip_s, snip_s, channels=ch, chunk_s=CHUNK_S,
+                                      plant_period_s=PLANT_PERIOD_S, plant_jitter_s=PLANT_JITTER_S)
+        cpu_sample._cache = ((wl, chunks), orc.pcm16_to_f32(pcm, ch), orc.pcm16_to_f32(snip, 1))
+    _, x, s = cpu_sample._cache
+    cfg = orc.make_config(CHUNK_S, len(s) / sr, distance_s, PROM)
+    t = time.perf_counter()
+    peaks = orc.calc_chunks(x, s, sr, cfg, scale=True, precision=precision, threads=cores, n_chunks=chunks)
+    return time.perf_counter() - t, peaks
+
+
+def run_reference(args, name, wl, out_stream):
+    """Each step is a bounded sample of the workload: one logical chunk per host thread."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import am_oracle as orc
     sr, ch, snip_s, hours, fft_log2, n_snip = wl
-    cores = min(os.cpu_count() or 1, orc.threads(), 32)
+    cores = host_cores()
     chunks = cores if args.sample_chunks <= 0 else args.sample_chunks
     stream_s = chunks * CHUNK_S
-    pcm, snip, _ = orc.synth_case(sr, stream_s + snip_s, snip_s, channels=ch, chunk_s=CHUNK_S,
-                                  plant_period_s=PLANT_PERIOD_S, plant_jitter_s=PLANT_JITTER_S)
-    x, s = orc.pcm16_to_f32(pcm, ch), orc.pcm16_to_f32(snip, 1)
-    cfg = orc.make_config(CHUNK_S, len(s) / sr, DIST_S, PROM)
     times = []
     for i in range(args.warmup + args.steps):
-        t = time.perf_counter()
-        peaks = orc.calc_chunks(x, s, sr, cfg, scale=True, precision=32, threads=cores, n_chunks=chunks)
-        dt = time.perf_counter() - t
+        dt, peaks = cpu_sample(wl, chunks, cores)
         if i >= args.warmup:
             times.append(dt)
-        log(f"[reference] step {i}: {dt:.2f}s, {len(peaks)} peaks")
+        log(f"[reference] step {i}: {dt:.2f}s, {len(peaks)} peaks, {cores} threads")
     total = sum(times)
     value = (stream_s / 3600.0) * len(times) / total / n_snip     # a batch is n_snip independent reference runs
-    sample = f"{chunks} logical chunks ({stream_s:.0f} s of {sr} Hz audio) of the {args.workload} workload per step, {cores} threads"
+    sample = (f"{chunks} logical chunks ({stream_s:.0f} s of {sr} Hz audio) of the {name} workload per step, {cores} threads "
+              f"(sched_getaffinity; OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS', 'unset')} ignored)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, wl), "note": "oracle port of the reference CPU path; Rust crate not buildable here"},
+        "config": {"workload": workload_name(name, wl),
+                   "note": "oracle port of the reference CPU path (exact-length scalar Bluestein/Stockham FFTs per chunk, snippet FFT "
+                           "recomputed per chunk); not rustfft-class -- see cpu_baseline.optimised_port in the b200 arm's line"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), file=out_stream, flush=True)
 
 
-def workload_name(args, wl):
-    sr, ch, snip_s, hours, fft_log2, n_snip = wl
-    return (f"{args.workload}: {'one' if n_snip == 1 else n_snip} {snip_s:g} s snippet{'s' if n_snip > 1 else ''} vs {hours:g} h {sr} Hz {'stereo' if ch == 2 else 'mono'} int16 "
-            f"stream per GPU, chunk 60 s, distance 480 s, prominence 0.13")
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+class Shard:
+    """One rank's share of a workload: matcher handle, synthetic PCM resident in HBM, expected offsets."""
+
+    def __init__(self, name, wl, world, rank, stream, distance_s=DIST_S, total_hours=None):
+        import numpy as np
+        import torch
+        import audio_matcher_b200 as am
+        from audio_matcher_b200 import _native as N
+        from audio_matcher_b200.matcher import shard_chunks
+        from oracle import am_oracle as orc   # workload constants (seeds, plant offsets) + checker only
+        self.name, self.wl, self.world, self.rank, self.stream = name, wl, world, rank, stream
+        sr, ch, snip_s, hours, fft_log2, n_snip = wl
+        self.sr, self.ch, self.n_snip = sr, ch, n_snip
+        self.m = m = int(round(snip_s * sr))
+        # weak scaling: `hours` per GPU; total_hours fixes the whole job instead (strong scaling)
+        self.total_frames = int(round((total_hours if total_hours else hours * world) * 3600 * sr))
+        self.conf = am.Config(chunk_size=CHUNK_S, overlap_length=-1.0, peak_config=am.PeakConfig(distance_s, PROM), fft_log2=fft_log2)
+        self.snips_np = [orc.synth_pcm16(orc.SEED_SNIP + i, 0, m) for i in range(n_snip)]
+        if n_snip == 1:
+            self.algo = am.CudaConvolve(self.snips_np[0], sr=sr, config=self.conf, stream=stream.cuda_stream)
+        else:
+            self.algo = am.CudaConvolve(np.stack([orc.pcm16_to_f32(x) for x in self.snips_np]), sr=sr, config=self.conf,
+                                        stream=stream.cuda_stream, batch=True)
+        total_chunks = self.algo.num_chunks(self.total_frames)
+        self.c0, self.nc = shard_chunks(total_chunks, world, rank)
+        self.lo, self.hi = self.algo.shard_frames(self.c0, self.nc, self.total_frames)
+        L = N.lib()
+        n = self.hi - self.lo
+        self.pcm = torch.empty((n, ch) if ch == 2 else (n,), dtype=torch.int16, device="cuda")
+        N.check(L.am_synth_pcm16_device(orc.SEED_STREAM, self.lo * ch, n * ch, self.pcm.data_ptr(), stream.cuda_stream))
+        snips_dev = [torch.from_numpy(x).cuda() for x in self.snips_np]
+        self.plan = plant_plan(sr, snip_s, self.total_frames)
+        for k, (o, shift) in enumerate(self.plan):             # occurrence k carries snippet k mod n_snip
+            if o + m <= self.lo or o >= self.hi:
+                continue
+            skip = max(0, self.lo - o)
+            N.check(L.am_synth_plant_device(self.pcm.data_ptr(), n, ch, snips_dev[k % n_snip].data_ptr() + 2 * skip, m - skip,
+                                            o + skip - self.lo, shift, stream.cuda_stream))
+        self.expected = {(o, k % n_snip) for k, (o, _) in enumerate(self.plan)}
+        torch.cuda.synchronize()
+
+    def step(self, samples):
+        if self.world == 1:
+            return self.algo._calc(samples, True, self.total_frames, self.lo, self.c0, self.nc, True, 1 << 16)
+        return self.algo.calc_chunks_sharded(samples, True, total_frames=self.total_frames, buf_first_frame=self.lo,
+                                             first_chunk=self.c0, num_chunks=self.nc, cap=1 << 16)
+
+    def timed(self, samples, warmup, steps, profile=False):
+        import torch
+        import torch.distributed as dist
+        for _ in range(warmup):
+            peaks = self.step(samples)
+        if profile:
+            self.algo.set_profiling(True)
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            peaks = self.step(samples)
+        e1.record(self.stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, peaks
+
+    def hours_total(self):
+        return self.total_frames / self.sr / 3600.0
+
+    def verify_vs_oracle(self, n_chunks=2):
+        """found == oracle on `n_chunks` consecutive logical chunks of this rank's shard (the first ones that hold a
+        planted occurrence, else the shard's first): the sub-stream is matched by the GPU path and by the CPU oracle
+        as a stream of its own, lists compared before the global filter.  -> (ok, chunks checked, first chunk)"""
+        import numpy as np
+        from oracle import am_oracle as orc
+        C_ = int(round(CHUNK_S * self.sr))
+        ov = self.m
+        first = self.c0
+        for o, _ in self.plan:
+            ci = o // C_
+            if self.c0 <= ci and ci + n_chunks <= self.c0 + self.nc:
+                first = ci
+                break
+        n_chunks = min(n_chunks, self.nc)
+        f0 = C_ * first - self.lo
+        f1 = min(self.hi - self.lo, f0 + C_ * n_chunks + ov)
+        sub = self.pcm[f0:f1]
+        got = self.algo._calc(sub, True, None, 0, 0, n_chunks, False, 1 << 14)
+        host = sub.cpu().numpy()
+        x = orc.pcm16_to_f32(host.reshape(-1), self.ch)
+        ok = True
+        for sn in range(min(self.n_snip, 2)):
+            s = orc.pcm16_to_f32(self.snips_np[sn], 1)
+            ref = orc.calc_chunks(x, s, self.sr, orc.make_config(CHUNK_S, len(s) / self.sr, self.conf.peak_config.distance, PROM),
+                                  scale=True, precision=32, threads=min(host_cores(), n_chunks), n_chunks=n_chunks, final_filter=False)
+            mine = sorted((p.chunk, p.position.start) for p in got if p.snippet_id == sn)
+            theirs = sorted((p.chunk, p.start) for p in ref)
+            ok = ok and mine == theirs
+            for a, b in zip(sorted((p for p in got if p.snippet_id == sn), key=lambda p: (p.chunk, p.position.start)),
+                            sorted(ref, key=lambda p: (p.chunk, p.start))):
+                ok = ok and abs(a.height - b.height) <= 1e-4 * abs(b.height) and abs(a.prominence - b.prominence) <= 1e-4 * abs(b.prominence)
+        return ok, n_chunks, first
+
+    def close(self):
+        import torch
+        self.algo.close()
+        self.pcm = None
+        torch.cuda.empty_cache()
+
+
+def model_bytes_per_step(frames, b_in, n_fft, m, n_snip):
+    """frames * (B_in + 8 + S (8 + 4 sigma)) * N / V_N.  sigma = 1 iff the S spectra (S * 8N bytes)
+    exceed what stays L2-resident (order 100 MB)."""
+    sigma = 1 if n_snip * 8 * n_fft > 100e6 else 0
+    vn = n_fft - m + 1
+    return frames * (b_in + 8 + n_snip * (8 + 4 * sigma)) * n_fft / vn, sigma
+
+
+def measure_config(name, wl, world, rank, stream, steps, warmup, distance_s=DIST_S, total_hours=None, verify_chunks=0):
+    """Compact record for `other_configs`: value, step time, model fraction, peak check."""
+    sh = Shard(name, wl, world, rank, stream, distance_s=distance_s, total_hours=total_hours)
+    ms, peaks = sh.timed(sh.pcm, warmup, steps, profile=True)
+    ktimes = sh.algo.kernel_times()
+    sh.algo.set_profiling(False)
+    stats = sh.algo.stats()
+    ms_per_step = ms / steps
+    value = sh.hours_total() / (ms_per_step / 1000.0)
+    starts = [(p.position.start, p.snippet_id) for p in peaks]
+    n_fft = 1 << stats["fft_log2"] if stats["fft_log2"] else 0
+    peak_gbs, _ = measured_hbm_peak()
+    mb, sigma = model_bytes_per_step(sh.hi - sh.lo, 2 * sh.ch, n_fft, sh.m, sh.n_snip) if n_fft else (0, 0)
+    rec = {"workload": workload_name(name, wl) if distance_s == DIST_S else f"{name}, --distance {distance_s:g} s",
+           "n_gpus": world, "hours_total": sh.hours_total(), "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps,
+           "fft_log2": stats["fft_log2"], "four_step": f"{1 << stats['log2_n1']}x{1 << stats['log2_n2']}",
+           "summary_mode": stats["summary_mode"], "dense_chunks": stats.get("dense_chunks", 0), "n_snippets": sh.n_snip,
+           "snippet_hours_per_s": value * sh.n_snip,
+           "model_frac_of_hbm": mb / (ms_per_step / 1000.0) / 1e9 / peak_gbs if mb else None, "model_sigma": sigma,
+           "peaks_found": len(starts), "planted": len(sh.plan),
+           "verified_offsets_are_planted": len(starts) > 0 and all(s in sh.expected for s in starts),
+           "kernel_ms_per_step": {k: round(v["total_ms"] / steps, 4) for k, v in ktimes.items()}}
+    if verify_chunks:
+        ok, nchk, first = sh.verify_vs_oracle(verify_chunks)
+        rec["verified_vs_oracle_chunks"] = nchk if ok else 0
+        rec["verified_vs_oracle_first_chunk"] = first
+    sh.close()
+    return rec
 
 
 def main():
@@ -199,6 +388,8 @@ def _main(out_stream):
     ap.add_argument("--sample-chunks", type=int, default=0, help="CPU baseline sample size in logical chunks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configs (other_configs)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the sampled-chunk comparison with the oracle")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.hours > 0:
@@ -207,101 +398,54 @@ def _main(out_stream):
         wl[4] = args.fft_log2
     wl = tuple(wl)
     if args.impl == "reference":
-        run_reference(args, wl, out_stream)
+        run_reference(args, args.workload, wl, out_stream)
         return
 
     import numpy as np
     import torch
     import torch.distributed as dist
-    import ctypes as C
-    import audio_matcher_b200 as am
-    from audio_matcher_b200 import _native as N
-    from audio_matcher_b200.matcher import shard_chunks, shard_frames, calc_chunks_sharded
-    from oracle import am_oracle as orc   # workload constants + CPU baseline only
+    import audio_matcher_b200 as am   # noqa: F401  (fails loudly if the CUDA library is missing)
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
     torch.cuda.set_device(local_rank)
+    comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sr, ch, snip_s, hours, fft_log2, n_snip = wl
-    m = int(round(snip_s * sr))
-    frames_per_gpu = int(round(hours * 3600 * sr))
-    total_frames = frames_per_gpu * world
-    conf = am.Config(chunk_size=CHUNK_S, overlap_length=-1.0, peak_config=am.PeakConfig(DIST_S, PROM), fft_log2=fft_log2)
-    snips_np = [orc.synth_pcm16(orc.SEED_SNIP + i, 0, m) for i in range(n_snip)]
+        from audio_matcher_b200.matcher import comm_init_from_torch
+        comm = comm_init_from_torch()                    # NCCL communicator of the C ABI (am_comm_init)
     stream = torch.cuda.current_stream()
-    if n_snip == 1:
-        algo = am.CudaConvolve(snips_np[0], sr=sr, config=conf, stream=stream.cuda_stream)
-    else:
-        algo = am.CudaConvolve(np.stack([orc.pcm16_to_f32(x) for x in snips_np]), sr=sr, config=conf,
-                               stream=stream.cuda_stream, batch=True)
-    total_chunks = algo.num_chunks(total_frames)
-    c0, nc = shard_chunks(total_chunks, world, rank)
-    lo, hi = shard_frames(c0, nc, total_frames, sr, conf, m)
+    sr, ch, snip_s, hours, fft_log2, n_snip = wl
 
-    # ---- synthetic shard, generated on the device (identical integers to the oracle's generator)
-    L = N.lib()
-    pcm = torch.empty(((hi - lo), ch) if ch == 2 else (hi - lo,), dtype=torch.int16, device="cuda")
-    N.check(L.am_synth_pcm16_device(orc.SEED_STREAM, lo * ch, (hi - lo) * ch, pcm.data_ptr(), stream.cuda_stream))
-    snips_dev = [torch.from_numpy(x).cuda() for x in snips_np]
-    plan = plant_plan(sr, snip_s, total_frames)
-    for k, (o, shift) in enumerate(plan):                  # occurrence k carries snippet k mod n_snip
-        if o + m <= lo or o >= hi:
-            continue
-        skip = max(0, lo - o)
-        N.check(L.am_synth_plant_device(pcm.data_ptr(), hi - lo, ch, snips_dev[k % n_snip].data_ptr() + 2 * skip, m - skip,
-                                        o + skip - lo, shift, stream.cuda_stream))
-    expected = {(o, k % n_snip) for k, (o, _) in enumerate(plan)}
-    torch.cuda.synchronize()
-
-    def step(samples):
-        if world == 1:
-            return algo._calc(samples, True, total_frames, lo, c0, nc, True, 1 << 16)
-        return calc_chunks_sharded(sr, samples, algo, True, conf, total_frames=total_frames, buf_first_frame=lo,
-                                   first_chunk=c0, num_chunks=nc, cap=1 << 14, set_config=False)
-
-    def timed(samples, warmup, steps, profile=False):
-        for _ in range(warmup):
-            peaks = step(samples)
-        if profile:
-            algo.set_profiling(True)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            peaks = step(samples)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, peaks
-
+    sh = Shard(args.workload, wl, world, rank, stream)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms, peaks = timed(pcm, args.warmup, args.steps, profile=True)
+    ms, peaks = sh.timed(sh.pcm, args.warmup, args.steps, profile=True)
     clocks = sampler.stop()
-    ktimes = algo.kernel_times()
-    algo.set_profiling(False)
-    stats = algo.stats()
+    ktimes = sh.algo.kernel_times()
+    sh.algo.set_profiling(False)
+    stats = sh.algo.stats()
     ms_per_step = ms / args.steps
-    value = (total_frames / sr / 3600.0) / (ms_per_step / 1000.0)
-    # sanity: every reported offset is a planted one (the oracle parity proper lives in tests/)
+    value = sh.hours_total() / (ms_per_step / 1000.0)
+    # sanity: every reported offset is a planted one; the oracle comparison proper is verify_vs_oracle + tests/
     starts = [(p.position.start, p.snippet_id) for p in peaks]
-    verified = len(starts) > 0 and all(s in expected for s in starts)
+    verified = len(starts) > 0 and all(s in sh.expected for s in starts)
+    vs_oracle = None
+    if not args.no_verify:
+        ok, nchk, first = sh.verify_vs_oracle(2)
+        vs_oracle = {"chunks": nchk if ok else 0, "first_chunk": first, "ok": ok}
+        if world > 1:
+            t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            vs_oracle["all_ranks_ok"] = bool(t.item() > 0.5)
 
     # ---- roofline of the dominant kernel (algorithmic bytes, SURVEY.md 8d / DESIGN.md)
     n_fft = 1 << stats["fft_log2"] if stats["fft_log2"] else 0
     b_in = 2 * ch
     pairs = (stats["fft_blocks"] + 1) // 2
-    sigma = 1 if n_snip * 8 * n_fft > 100e6 else 0          # snippet spectra resident in L2 or not
+    step_model_bytes, sigma = model_bytes_per_step(sh.hi - sh.lo, b_in, n_fft, sh.m, n_snip) if n_fft else (0, 0)
     model_bytes = {
         "k_col_fwd": pairs * (2 * n_fft * b_in + 8 * n_fft),
         "k_row": pairs * n_fft * (16 if n_snip == 1 else 16 + n_snip * (16 + 8 * sigma)),
@@ -314,82 +458,142 @@ def _main(out_stream):
     if dom:
         per_step_ms = ktimes[dom]["total_ms"] / args.steps
         achieved = model_bytes[dom] / (per_step_ms / 1000.0) / 1e9
-        traffic = None
-        if stats["fft_log2"] == 22 and n_snip == 1 and dom in NCU_DRAM_BYTES_PER_PAIR_2P22:
-            traffic = NCU_DRAM_BYTES_PER_PAIR_2P22[dom] * pairs / (ktimes[dom]["launches"] / args.steps)   # per launch
+        traffic, sha = None, kernel_src_sha16()
+        tsrc = f"stale: kernel sources {sha} differ from the ncu capture's ({NCU_TRAFFIC['kernel_src_sha16'] or 'none'})"
+        if stats["fft_log2"] == 22 and n_snip == 1 and dom in NCU_TRAFFIC["bytes_per_pair"] and NCU_TRAFFIC["kernel_src_sha16"] == sha:
+            traffic = NCU_TRAFFIC["bytes_per_pair"][dom] * pairs / (ktimes[dom]["launches"] / args.steps)   # per launch
+            tsrc = f"ncu dram bytes per block pair ({NCU_TRAFFIC['file']}) x pairs per launch"
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                    "frac": achieved / peak_gbs, "traffic": traffic,
-                    "traffic_source": "ncu dram bytes per block pair (profiles/r01_ncu_full_streaming.csv) x pairs per launch",
+                    "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": tsrc,
                     "algorithmic_bytes_per_launch": model_bytes[dom] / (ktimes[dom]["launches"] / args.steps),
-                    "peak_source": peak_src,
-                    "launches_per_step": ktimes[dom]["launches"] / args.steps, "ms_per_step": per_step_ms,
-                    "algorithmic_bytes_per_step": model_bytes[dom]}
-    vn = n_fft - m + 1 if n_fft else 1
-    step_model_bytes = (hi - lo) * (b_in + 8 + n_snip * (8 + 4 * sigma)) * n_fft / vn if n_fft else 0
+                    "peak_source": peak_src, "launches_per_step": ktimes[dom]["launches"] / args.steps,
+                    "ms_per_step": per_step_ms, "algorithmic_bytes_per_step": model_bytes[dom]}
     kernel_share = {k: round(v["total_ms"] / args.steps, 4) for k, v in ktimes.items()}
 
-    # ---- end to end: PCM in pinned host memory, H2D inside the timed region
+    # ---- end to end: PCM in host memory, H2D inside the timed region, peak list read back
     e2e = None
     if not args.no_e2e:
         near = bind_near_gpu(local_rank) if world > 1 else None      # several ranks share the host: keep uploads NUMA-local
-        host = torch.empty(pcm.shape, dtype=torch.int16, pin_memory=True)
-        host.copy_(pcm)
+        host = torch.empty(sh.pcm.shape, dtype=torch.int16, pin_memory=True)
+        host.copy_(sh.pcm)
         torch.cuda.synchronize()
-        e_ms, e_peaks = timed(host, min(args.warmup, 2), args.steps)
-        est = algo.stats()
-        e_value = (total_frames / sr / 3600.0) / (e_ms / args.steps / 1000.0)
+        e_ms, e_peaks = sh.timed(host, min(args.warmup, 2), args.steps)
+        est = sh.algo.stats()
+        e_step_s = e_ms / args.steps / 1000.0
         verified = verified and [(p.position.start, p.snippet_id) for p in e_peaks] == starts
-        e2e = {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": est["h2d_bytes"], "d2h_bytes_per_step": est["d2h_bytes"],
-               "ms_per_step": e_ms / args.steps, "host_cpus_near_gpu": near}
+        h2d_gbs = est["h2d_bytes"] / e_step_s / 1e9
+        agg = h2d_gbs
+        if world > 1:
+            t = torch.tensor([h2d_gbs], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            agg = float(t.item())
+        e2e = {"value": sh.hours_total() / e_step_s, "unit": UNIT, "h2d_bytes_per_step": est["h2d_bytes"],
+               "d2h_bytes_per_step": est["d2h_bytes"], "ms_per_step": e_ms / args.steps, "host_memory": "pinned int16",
+               "host_cpus_near_gpu": near, "h2d_gbs_per_gpu": h2d_gbs, "h2d_gbs_aggregate": agg,
+               "limiter": "host-to-device copies (PCIe per GPU; with N > 1 the ranks share one host's memory fabric)"}
+        # what the drop-in shim's callers hold: pageable Vec<i16> (a decoder's output) and pageable Vec<f32>
+        # (ffi/cuda_convolve.rs collects the reference's f32 iterator); fewer steps, they are slow
+        variants = []
+        if world == 1:
+            v_steps = max(1, min(3, args.steps))
+            host_np = host.numpy()
+            for label, arr in (("pageable int16 (Vec<i16>)", np.array(host_np, copy=True)),
+                               ("pageable f32 (Vec<f32>, what ffi/cuda_convolve.rs passes)", None)):
+                if arr is None:
+                    if ch != 1:
+                        continue
+                    arr = host_np.astype(np.float32) * np.float32(1.0 / 65535.0)
+                v_ms, v_peaks = sh.timed(arr, 1, v_steps)
+                vst = sh.algo.stats()
+                v_s = v_ms / v_steps / 1000.0
+                variants.append({"host_memory": label, "value": sh.hours_total() / v_s, "unit": UNIT, "ms_per_step": v_ms / v_steps,
+                                 "h2d_bytes_per_step": vst["h2d_bytes"], "h2d_gbs": vst["h2d_bytes"] / v_s / 1e9, "steps": v_steps,
+                                 "offsets_equal": [(p.position.start, p.snippet_id) for p in v_peaks] == starts})
+                del arr
+            e2e["variants"] = variants
         del host
+
+    frames_here = sh.hi - sh.lo
+    peaks_found, planted = len(starts), len(sh.plan)
+    sh.close()
+
+    # ---- the other BASELINE configs, bounded: driver-visible in the same line
+    others = []
+    if not args.no_others and args.workload == "cfg2" and args.hours == 0:
+        def add(fn):
+            try:
+                others.append(fn())
+            except Exception as e:                                   # one config failing must not lose the headline line
+                others.append({"error": f"{type(e).__name__}: {e}"})
+                log("other config failed:", e)
+        if world == 1:
+            add(lambda: measure_config("cfg1", WORKLOADS["cfg1"], 1, 0, stream, 10, 3, verify_chunks=0 if args.no_verify else 2))
+            for d in (8.0, 20.0, 60.0, 120.0):                      # benches/my_benchmark.rs:95, --distance sweep on cfg 1
+                add(lambda d=d: measure_config("cfg1", WORKLOADS["cfg1"], 1, 0, stream, 10, 3, distance_s=d))
+            add(lambda: measure_config("cfg3", WORKLOADS["cfg3"], 1, 0, stream, 2, 1))
+            add(lambda: measure_config("cfg4", WORKLOADS["cfg4"], 1, 0, stream, 3, 2, verify_chunks=0 if args.no_verify else 2))
+            add(lambda: measure_config("cfg5", WORKLOADS["cfg5"], 1, 0, stream, 5, 2, verify_chunks=0 if args.no_verify else 2))
+        else:
+            # cfg 4: 125 h per GPU = the BASELINE-named 1000 h archive at 8 GPUs; cfg 5: the 100 h stream split N ways
+            add(lambda: measure_config("cfg4", WORKLOADS["cfg4"], world, rank, stream, 3, 2))
+            add(lambda: measure_config("cfg5", WORKLOADS["cfg5"], world, rank, stream, 5, 2, total_hours=100.0))
 
     if rank != 0:
         if world > 1:
+            if comm is not None:
+                comm.close()
             dist.destroy_process_group()
         return
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = min(os.cpu_count() or 1, orc.threads(), 32)
+        cores = host_cores()
         chunks = cores if args.sample_chunks <= 0 else args.sample_chunks
-        spcm, ssnip, _ = orc.synth_case(sr, chunks * CHUNK_S + snip_s, snip_s, channels=ch, chunk_s=CHUNK_S,
-                                        plant_period_s=PLANT_PERIOD_S, plant_jitter_s=PLANT_JITTER_S)
-        x, s = orc.pcm16_to_f32(spcm, ch), orc.pcm16_to_f32(ssnip, 1)
-        t = time.perf_counter()
-        orc.calc_chunks(x, s, sr, orc.make_config(CHUNK_S, len(s) / sr, DIST_S, PROM), scale=True, precision=32,
-                        threads=cores, n_chunks=chunks)
-        dt = time.perf_counter() - t
+        dt, _ = cpu_sample(wl, chunks, cores, precision=32)
         cpu_baseline = {"value": (chunks * CHUNK_S / 3600.0) / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{chunks} logical chunks ({chunks * CHUNK_S:.0f} s of audio) of this workload, "
-                                  f"exact-length f32 FFTs per chunk like the reference, {dt:.1f} s wall"}
+                                  f"exact-length f32 FFTs per chunk like the reference, {dt:.1f} s wall",
+                        "note": "scalar any-length FFT port (Bluestein for the prime length 3,839,999), memory-bound beyond ~16 threads; "
+                                "not rustfft-class -- optimised_port is the fairer CPU line"}
         # second CPU line: same semantics with power-of-two transforms and a cached snippet spectrum,
         # so the comparison is not inflated by the reference's exact-length transforms
-        t = time.perf_counter()
-        orc.calc_chunks(x, s, sr, orc.make_config(CHUNK_S, len(s) / sr, DIST_S, PROM), scale=True, precision=33,
-                        threads=cores, n_chunks=chunks)
-        dt2 = time.perf_counter() - t
+        dt2, _ = cpu_sample(wl, chunks, cores, precision=33)
         cpu_baseline["optimised_port"] = {"value": (chunks * CHUNK_S / 3600.0) / dt2, "unit": UNIT, "cores": cores,
                                           "note": f"power-of-two f32 FFTs + cached snippet spectrum, same sample, {dt2:.1f} s wall"}
+        if not args.no_others and args.workload == "cfg2":
+            # the CPU baseline's own config is cfg 1 (44.1 kHz, exact length 3,527,999 = 241 x 14639)
+            c1 = WORKLOADS["cfg1"]
+            n1 = min(chunks, 60)
+            sweep = {}
+            for d in (DIST_S, 8.0, 20.0, 60.0, 120.0):
+                dtd, pk = cpu_sample(c1, n1, cores, precision=32, distance_s=d)
+                sweep[f"{d:g}"] = {"value": (n1 * CHUNK_S / 3600.0) / dtd, "wall_s": round(dtd, 2), "peaks": len(pk)}
+            cpu_baseline["cfg1"] = {"unit": UNIT, "cores": cores, "sample": f"{n1} of cfg 1's 60 logical chunks", "by_distance_s": sweep}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args, wl), "fft_log2": stats["fft_log2"],
-                   "four_step": f"{1 << stats['log2_n1']}x{1 << stats['log2_n2']}", "frames_per_gpu": hi - lo,
-                   "peak_pass": {0: "dense correlation", 1: "run summaries", 2: "run summaries rejected, dense repeat"}[stats["summary_mode"]],
-                   "l2_policy": "inputs larger than L2 (PCM per GPU %.1f GB)" % ((hi - lo) * b_in / 1e9),
+        "config": {"workload": workload_name(args.workload, wl), "fft_log2": stats["fft_log2"],
+                   "four_step": f"{1 << stats['log2_n1']}x{1 << stats['log2_n2']}", "frames_per_gpu": frames_here,
+                   "peak_pass": {0: "dense correlation", 1: "run summaries", 2: "run summaries, some chunks repeated densely"}[stats["summary_mode"]],
+                   "dense_chunks": stats.get("dense_chunks", 0),
+                   "l2_policy": "inputs larger than L2 (PCM per GPU %.1f GB)" % (frames_here * b_in / 1e9),
                    "n_snippets": n_snip, "snippet_hours_per_s": value * n_snip,
-                   "peaks_found": len(starts), "planted": len(plan), "verified_offsets_are_planted": verified,
+                   "peaks_found": peaks_found, "planted": planted, "verified_offsets_are_planted": verified,
+                   "verified_vs_oracle_chunks": vs_oracle,
+                   "multi_gpu_merge": "ncclAllGather inside am_calc_chunks_sharded (C ABI)" if world > 1 else None,
                    "model_bytes_per_step": step_model_bytes,
                    "model_gbs": step_model_bytes / (ms_per_step / 1000.0) / 1e9,
                    "model_frac_of_hbm": step_model_bytes / (ms_per_step / 1000.0) / 1e9 / peak_gbs,
-                   "kernel_ms_per_step": kernel_share},
+                   "kernel_ms_per_step": kernel_share, "kernel_src_sha16": kernel_src_sha16()},
         "clocks": clocks, "e2e": e2e, "gpu_launches": stats["kernel_launches"] * args.steps,
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "other_configs": others,
     }
     print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
 
 

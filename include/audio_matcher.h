@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define AM_ABI_VERSION 1
+#define AM_ABI_VERSION 2
 
 typedef enum {
     AM_OK = 0,
@@ -84,8 +84,8 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t fft_log2, log2_n1, log2_n2;   /* block length and its four-step split (n1 = 1 => single pass) */
     uint32_t chunks;
-    uint32_t summary_mode;      /* 0 dense correlation, 1 run summaries, 2 summaries rejected -> repeated densely */
-    uint32_t reserved;
+    uint32_t summary_mode;      /* 0 dense correlation, 1 run summaries, 2 run summaries + some chunks repeated densely */
+    uint32_t dense_chunks;      /* summary mode: logical chunks whose peak search was repeated on a dense correlation */
 } am_stats;
 
 /* kernel classes for the optional per-kernel device timing */
@@ -101,6 +101,18 @@ typedef struct {
 } am_kernel_time;
 
 typedef struct am_matcher am_matcher;
+
+/* Optional progress callback, the C shape of the two Once callbacks per chunk the reference feeds its progress
+ * bar with (audio_matcher.rs:102-117,129).  Fired from the thread that called am_calc_chunks*: phase 0 when the
+ * work of logical chunks [first_chunk, first_chunk + n_chunks) has been submitted to the GPU (one call per
+ * segment), phase 1 once when the peaks of the whole call are final.  Must not call back into the library. */
+typedef void (*am_progress_fn)(void *user, int phase, size_t first_chunk, size_t n_chunks);
+
+/* Multi-GPU communicator (one process per GPU): wraps an NCCL communicator that am_calc_chunks_sharded uses for
+ * the one exchange step of the path, the merge of per-shard peak candidates (audio_matcher.rs:132-139).  NCCL is
+ * loaded at run time (libnccl.so.2, the copy already in the process if there is one). */
+typedef struct am_comm am_comm;
+#define AM_COMM_ID_BYTES 128   /* sizeof(ncclUniqueId) */
 
 const char *am_last_error(void);
 int am_abi_version(void);
@@ -135,6 +147,9 @@ am_status am_matcher_get_stats(const am_matcher *h, am_stats *out);
 am_status am_matcher_set_profiling(am_matcher *h, int on);
 am_status am_matcher_get_kernel_times(const am_matcher *h, am_kernel_time *out, size_t cap, size_t *n_out);
 
+/* progress callback (NULL = none, the default) */
+am_status am_matcher_set_progress(am_matcher *h, am_progress_fn fn, void *user);
+
 /* CorrelateAlgo::inverse_sample_auto_correlation (audio_matcher.rs:66,321-329): 1 / sum(s^2) */
 am_status am_inverse_sample_auto_correlation(am_matcher *h, float *out);
 
@@ -149,6 +164,14 @@ am_status am_correlate(am_matcher *h, const void *within, size_t n, am_sample_fm
 
 /* number of logical chunks calc_chunks makes of a stream (audio_matcher.rs:99-104) */
 size_t am_num_chunks(const am_matcher *h, size_t frames);
+
+/* chunk geometry in samples as calc_chunks derives it (audio_matcher.rs:99-100): chunk = round(chunk_size * sr),
+ * overlap = round(overlap_length * sr), f64::round = half away from zero */
+am_status am_chunk_geometry(const am_matcher *h, size_t *chunk, size_t *overlap);
+/* frames [*lo, *hi) of a stream of total_frames frames that logical chunks [first_chunk, first_chunk + num_chunks)
+ * read: the chunks themselves plus the overlap halo (the shard a rank has to hold) */
+am_status am_shard_frames(const am_matcher *h, size_t total_frames, size_t first_chunk, size_t num_chunks, size_t *lo,
+                          size_t *hi);
 
 /* calc_chunks (audio_matcher.rs:88-141): the fused path -- correlation, per-chunk peak
  * finding (min prominence, min distance), global sort and neighbour filter.  Peaks come
@@ -170,6 +193,24 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
  * over peaks gathered from all shards; host-only, `peaks` is reordered in place. */
 am_status am_merge_peaks(am_peak *peaks, size_t n, uint32_t sr, double distance_s, am_peak *out, size_t cap,
                          size_t *n_out);
+
+/* ---- multi-GPU: one process per GPU, chunk-range shards, one all-gather of peak candidates ----------------
+ * am_comm_get_unique_id: rank 0 creates the 128-byte id and hands it to the other ranks by any means (file, MPI,
+ * torch.distributed ...); am_comm_init is collective over the nranks processes and binds the communicator to the
+ * CURRENT CUDA device. */
+am_status am_comm_get_unique_id(void *id_out /* AM_COMM_ID_BYTES */);
+am_status am_comm_init(int nranks, int rank, const void *nccl_unique_id, am_comm **out);
+void am_comm_destroy(am_comm *comm);
+int am_comm_rank(const am_comm *comm);
+int am_comm_size(const am_comm *comm);
+/* calc_chunks over a stream sharded by logical-chunk ranges: this rank runs chunks [first_chunk, first_chunk +
+ * num_chunks) on the frames it holds (am_shard_frames: its chunks + the overlap halo, no halo exchange); the
+ * device-resident peak lists and counts of all ranks are exchanged with ONE ncclAllGather of fixed-size records
+ * (a second one only if a rank overflows the record), and every rank applies the global sort + neighbour filter
+ * (am_merge_peaks) and gets the complete result.  Collective: every rank of `comm` must call it. */
+am_status am_calc_chunks_sharded(am_matcher *h, am_comm *comm, const void *stream, size_t buf_first_frame,
+                                 size_t buf_frames, size_t total_frames, am_sample_fmt fmt, am_mem mem, int scale,
+                                 size_t first_chunk, size_t num_chunks, am_peak *out, size_t cap, size_t *n_out);
 
 /* is_overshadowed (audio_matcher.rs:143-160); other == NULL is None */
 int am_is_overshadowed(const am_peak *element, const am_peak *other, uint32_t sr, double max_distance_s);

@@ -117,6 +117,65 @@ template <int LOG2N, int E = 16> static double check_roundtrip() {
     return bad ? 1.0 : maxerr;
 }
 
+// stage 0 with geometric input twiddles (RegFFT::butterfly0_geo, the inverse column pass): element r of
+// butterfly l of thread t is multiplied by base[t][l] * step[t]^r before the transform
+template <class F, int ST> struct RunnerFrom1 {
+    static constexpr int EPT = F::EPT;
+    static void go(std::vector<float2> &regs, std::vector<float2> &sm) {
+        constexpr int GT = F::GT;
+        if constexpr (ST > 0)
+            for (int t = 0; t < GT; ++t) F::template butterfly<ST>(*(float2(*)[EPT]) & regs[t * EPT], t, g_tw.data());
+        if constexpr (ST + 1 < F::NST) {
+            for (int t = 0; t < GT; ++t) F::template xchg_write<ST>(*(const float2(*)[EPT]) & regs[t * EPT], sm.data(), t);
+            for (int t = 0; t < GT; ++t) F::template xchg_read<ST + 1>(*(float2(*)[EPT]) & regs[t * EPT], sm.data(), t);
+            RunnerFrom1<F, ST + 1>::go(regs, sm);
+        }
+    }
+};
+template <int LOG2N, int LOG2B, int E> static double check_geo() {
+    typedef RegFFT<LOG2N, LOG2B, true, E> F;
+    constexpr int N = F::N, B = F::B, GT = F::GT, EPT = E, RB = F::bits_at(0), R = 1 << RB, NB = EPT / R;
+    std::vector<float2> x(N * B);
+    for (auto &e : x) e = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+    std::vector<cd> xt(N * B);                       // twiddled inputs in double
+    std::vector<float2> regs(GT * EPT), sm(F::SMEM_ELEMS, make_float2(NAN, NAN));
+    for (int t = 0; t < GT; ++t) {
+        float2 base[NB];
+        const double as = 0.37 * (t % 7 + 1) / R;
+        const float2 step = make_float2((float)cos(as), (float)sin(as));
+        for (int l = 0; l < NB; ++l) {
+            const double ab = 0.11 * (t + 3 * l);
+            base[l] = make_float2((float)(0.5 * cos(ab)), (float)(0.5 * sin(ab)));
+            for (int r = 0; r < R; ++r) {
+                int idx, c;
+                F::template in_coord<0>(t, l * R + r, idx, c);
+                regs[t * EPT + l * R + r] = x[idx * B + c];
+                xt[idx * B + c] = cd(x[idx * B + c].x, x[idx * B + c].y) * cd(base[l].x, base[l].y) * std::pow(cd(step.x, step.y), r);
+            }
+        }
+        F::butterfly0_geo(*(float2(*)[EPT]) & regs[t * EPT], base, step);
+    }
+    RunnerFrom1<F, 0>::go(regs, sm);
+    double maxerr = 0, maxref = 0;
+    for (int c = 0; c < B; ++c) {
+        std::vector<cd> a(N);
+        for (int i = 0; i < N; ++i) a[i] = xt[i * B + c];
+        ref_fft(a, true);
+        for (int t = 0; t < GT; ++t)
+            for (int j = 0; j < EPT; ++j) {
+                int idx, cc;
+                F::out_coord(t, j, idx, cc);
+                if (cc != c) continue;
+                double e = std::abs(a[idx] - cd(regs[t * EPT + j].x, regs[t * EPT + j].y));
+                if (!(e <= maxerr)) maxerr = e;
+                maxref = std::max(maxref, std::abs(a[idx]));
+            }
+    }
+    double rel = maxerr / maxref;
+    printf("geo-twiddled stage 0: log2n=%d log2b=%d ept=%d radix0=%d  max_rel_err=%.3g %s\n", LOG2N, LOG2B, E, R, rel, rel < 2e-6 ? "OK" : "FAIL");
+    return rel;
+}
+
 int main() {
     g_tw.resize(TW_N);
     for (int j = 0; j < TW_N; ++j) {
@@ -137,6 +196,12 @@ int main() {
     worst = std::max(worst, check_roundtrip<12, 32>());
     worst = std::max(worst, check_roundtrip<13, 32>());
     worst = std::max(worst, check_roundtrip<14, 32>());
+    worst = std::max(worst, check_geo<9, 4, 32>());
+    worst = std::max(worst, check_geo<9, 4, 16>());
+    worst = std::max(worst, check_geo<10, 3, 16>());
+    worst = std::max(worst, check_geo<7, 4, 16>());
+    worst = std::max(worst, check_geo<8, 4, 16>());
+    worst = std::max(worst, check_geo<5, 6, 16>());
     printf(worst < 2e-6 ? "ALL OK\n" : "SOME FAILED\n");
     return worst < 2e-6 ? 0 : 1;
 }

@@ -262,6 +262,108 @@ def test_batch_equals_independent_runs(am, orc):
     batch.close()
 
 
+def _two_chunk_case(orc, sr, snippet_s, channels, seed, plant_at):
+    """A stream of two logical 60 s chunks (+ overlap) at one of BASELINE.json's geometries with the snippet planted
+    at `plant_at` (frame offsets, gains 1, 1/2, 1/4 cycling)."""
+    m, Cs = int(round(snippet_s * sr)), 60 * sr
+    frames = 2 * Cs + m
+    pcm = orc.synth_pcm16(orc.SEED_STREAM + seed, 0, frames * channels)
+    snip = orc.synth_pcm16(orc.SEED_SNIP + seed, 0, m)
+    for k, o in enumerate(plant_at):
+        orc.synth_plant(pcm, channels, snip, o, k % 3)
+    return pcm, snip, m, frames
+
+
+def test_cfg4_geometry_vs_oracle(am, orc):
+    """BASELINE.json configs[3] geometry: 44.1 kHz, 30 s snippet (m = 1,323,000), block 2^23 = 512 x 16384
+    (k_row32<14>, k_col_inv<9,4,32,14>, the TMA-fed forward column kernel with 16384-frame rows): calc_chunks over two
+    logical chunks against the oracle (audio_matcher.rs:88-141, 221-230)."""
+    import torch
+    sr = 44100
+    pcm, snip, m, frames = _two_chunk_case(orc, sr, 30.0, 1, 4, [700_001, 60 * sr + 1_234_567])
+    conf = am.Config(chunk_size=60.0, peak_config=am.PeakConfig(480.0, 0.13), fft_log2=23)
+    algo = am.CudaConvolve(snip, sr=sr, config=conf)
+    got = algo._calc(torch.from_numpy(pcm).cuda(), True, None, 0, 0, None, False, 1 << 12)
+    st = algo.stats()
+    algo.close()
+    assert (st["fft_log2"], st["log2_n1"], st["log2_n2"]) == (23, 9, 14) and st["summary_mode"] == 1
+    x, s = orc.pcm16_to_f32(pcm), orc.pcm16_to_f32(snip)
+    ref = orc.calc_chunks(x, s, sr, orc.make_config(60.0, m / sr, 480.0, 0.13), scale=True, precision=64, threads=3,
+                          final_filter=False)
+    assert len(ref) == 2
+    _assert_peaks(sorted(got, key=lambda p: (p.chunk, -p.height)), [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+
+
+def test_cfg5_geometry_vs_oracle(am, orc):
+    """BASELINE.json configs[4] geometry: stereo 96 kHz, 2 s snippet (m = 192,000), block 2^20 = 128 x 8192, downmix
+    (l + r) * 0.5 / 65535 fused into the TMA-fed column loads (mp3_reader.rs:12,35)."""
+    import torch
+    sr = 96000
+    pcm, snip, m, frames = _two_chunk_case(orc, sr, 2.0, 2, 5, [3_000_017, 60 * sr + 2_500_000, 60 * sr - 100_000])
+    conf = am.Config(chunk_size=60.0, peak_config=am.PeakConfig(480.0, 0.13), fft_log2=20)
+    algo = am.CudaConvolve(snip, sr=sr, config=conf)
+    got = algo._calc(torch.from_numpy(pcm.reshape(-1, 2)).cuda(), True, None, 0, 0, None, False, 1 << 12)
+    st = algo.stats()
+    algo.close()
+    assert (st["fft_log2"], st["log2_n1"], st["log2_n2"]) == (20, 7, 13)
+    x, s = orc.pcm16_to_f32(pcm, 2), orc.pcm16_to_f32(snip)
+    ref = orc.calc_chunks(x, s, sr, orc.make_config(60.0, m / sr, 480.0, 0.13), scale=True, precision=64, threads=3,
+                          final_filter=False)
+    assert len(ref) >= 2
+    _assert_peaks(sorted(got, key=lambda p: (p.chunk, -p.height)), [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+
+
+def test_batch_of_8_snippets_at_full_block_length(am, orc):
+    """BASELINE.json configs[2] at its real geometry: 8 snippets of 10 s at 48 kHz, block 2^22, i.e. the shared forward
+    passes + the default persistent inverse-only row kernel (k_row32_stream<13, ROW_INVERSE>) per snippet.  Every
+    snippet must find exactly its planted copies; three of them are checked against the oracle score for score."""
+    import torch
+    sr, m, Cs = 48000, 480000, 60 * 48000
+    frames = 2 * Cs + m
+    pcm = orc.synth_pcm16(orc.SEED_STREAM + 8, 0, frames)
+    snips = [orc.synth_pcm16(orc.SEED_SNIP + 80 + i, 0, m) for i in range(8)]
+    planted = {}
+    for i in range(8):                                                     # one copy per snippet, spread over both chunks
+        o = 200_003 + i * 610_007
+        orc.synth_plant(pcm, 1, snips[i], o, i % 2)
+        planted[i] = o
+    conf = am.Config(chunk_size=60.0, peak_config=am.PeakConfig(480.0, 0.13), fft_log2=22)
+    batch = am.CudaConvolve(np.stack([orc.pcm16_to_f32(s) for s in snips]), sr=sr, config=conf, batch=True)
+    got = batch._calc(torch.from_numpy(pcm).cuda(), True, None, 0, 0, None, False, 1 << 12)
+    st = batch.stats()
+    batch.close()
+    assert st["fft_log2"] == 22 and st["log2_n2"] == 13
+    for i in range(8):
+        assert [p.position.start for p in got if p.snippet_id == i] == [planted[i]], (i, [(p.snippet_id, p.position.start) for p in got])
+    x = orc.pcm16_to_f32(pcm)
+    for i in (0, 3, 7):
+        ref = orc.calc_chunks(x, orc.pcm16_to_f32(snips[i]), sr, orc.make_config(60.0, m / sr, 480.0, 0.13), scale=True,
+                              precision=64, threads=3, final_filter=False)
+        _assert_peaks([p for p in got if p.snippet_id == i], [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+
+
+def test_progress_callback_and_shard_geometry(am, orc):
+    """The progress callbacks of audio_matcher.rs:102-117,129 (segment submitted / call finished) and the library's own
+    shard geometry (am_shard_frames == the Python helper, including a .5 rounding case)."""
+    sr = 8000
+    pcm, snip, _ = orc.synth_case(sr, 40.0, 0.5, chunk_s=5.0, plant_period_s=12.5, plant_jitter_s=2.5)
+    conf = am.Config(chunk_size=5.0, peak_config=am.PeakConfig(2.0, 0.13))
+    algo = am.CudaConvolve(snip, sr=sr, config=conf)
+    seen = []
+    algo.set_progress(lambda phase, c0, nc: seen.append((phase, c0, nc)))
+    got = am.calc_chunks(sr, pcm, algo, True, conf)
+    algo.set_progress(None)
+    assert len(got) > 0 and seen[-1] == (1, 0, 8) and sum(nc for ph, c0, nc in seen if ph == 0) == 8
+    from audio_matcher_b200.matcher import shard_frames
+    for conf2 in (conf, am.Config(chunk_size=2.5, overlap_length=53 / 128, peak_config=am.PeakConfig(2.0, 0.13))):
+        algo.set_config(conf2)                                            # 53/128 s * 8000 = 3312.5 exactly: f64::round gives 3313, round-half-even 3312
+        C_, ov = algo.chunk_geometry()
+        assert (C_, ov) == ((40000, 4000) if conf2 is conf else (20000, 3313))
+        for c0, nc in ((0, 3), (2, 2), (5, 100)):
+            assert algo.shard_frames(c0, nc, len(pcm)) == shard_frames(c0, min(nc, algo.num_chunks(len(pcm)) - c0), len(pcm), sr, conf2, algo.m)
+    algo.close()
+
+
 def _peaks_from_correlation(am, native, c, m, C_, ov, prom, dist, summary, maxpk=0):
     """tests-only hook: per-chunk peak kernels on a supplied correlation (sr = 1, so seconds == samples)."""
     conf = am.Config(chunk_size=float(C_), overlap_length=float(ov), peak_config=am.PeakConfig(float(dist), prom),
@@ -499,6 +601,21 @@ def test_c_abi_from_plain_c(am, native, tmp_path):
     assert out.returncode == 0 and "capi_smoke ok" in out.stdout, out.stderr
 
 
+def test_two_gpu_sharded_c_abi(am, tmp_path):
+    """am_comm_init + am_calc_chunks_sharded from two plain processes (one per GPU), the NCCL unique id handed over in a
+    file: every rank must return the single-GPU result of the whole stream (tests/two_rank_sharded.py)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "two_rank_sharded.py"), str(r), "2", str(tmp_path / "nccl_id")],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "sharded ok" in o, f"rank {r}: {o[-2000:]}"
+
+
 def test_two_gpu_sharded_nccl(am):
     import torch
     if torch.cuda.device_count() < 2:
@@ -512,3 +629,4 @@ def test_two_gpu_sharded_nccl(am):
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["n_gpus"] == 2 and line["config"]["verified_offsets_are_planted"]
+    assert line["config"]["verified_vs_oracle_chunks"]["all_ranks_ok"]

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(native):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in audio_matcher.h but not exported"
     assert declared == set(native.SYMBOLS), declared ^ set(native.SYMBOLS)
-    assert native.lib().am_abi_version() == 1
+    assert native.lib().am_abi_version() == native.ABI_VERSION
 
 
 def test_struct_layouts(native):

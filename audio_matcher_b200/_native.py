@@ -78,6 +78,10 @@ SYMBOLS = {
     "am_num_chunks": (_SZ, [_VP, _SZ]),
     "am_chunk_geometry": (C.c_int, [_VP, C.POINTER(_SZ), C.POINTER(_SZ)]),
     "am_shard_frames": (C.c_int, [_VP, _SZ, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_SZ)]),
+    "am_stream_begin": (C.c_int, [_VP, _SZ, C.c_int, C.c_int, C.POINTER(_VP)]),
+    "am_stream_push": (C.c_int, [_VP, _VP, _SZ]),
+    "am_stream_finish": (C.c_int, [_VP, C.POINTER(AmPeak), _SZ, C.POINTER(_SZ)]),
+    "am_stream_abort": (None, [_VP]),
     "am_comm_get_unique_id": (C.c_int, [_VP]),
     "am_comm_init": (C.c_int, [C.c_int, C.c_int, _VP, C.POINTER(_VP)]),
     "am_comm_destroy": (None, [_VP]),

@@ -20,6 +20,8 @@
 #include <thread>
 #include <vector>
 
+#include <condition_variable>
+
 #include <cuda.h>
 #include <dlfcn.h>
 
@@ -90,48 +92,119 @@ template <class T> struct DevBuf {
 
 }  // namespace
 
-// Upload of PAGEABLE host memory (what a Vec / numpy caller hands over).  cudaMemcpyAsync stages such memory inside the
-// driver at ~11 GB/s; here a few host threads copy 32 MB chunks into a small ring of pinned buffers and each chunk
-// goes out with an asynchronous copy while the next one is being filled.  Pinned / registered memory never comes here.
+// Upload of PAGEABLE host memory (what a Vec / numpy caller or a decoder thread hands over).  cudaMemcpyAsync stages
+// such memory inside the driver at ~11 GB/s; here a persistent pool of host threads copies 32 MB chunks into a small
+// ring of pinned buffers and each chunk goes out with ONE asynchronous copy while the next one is being filled.
+// Pinned / registered memory handed to the one-shot entry points never comes here.
 struct HostStager {
     static constexpr size_t CHUNK = (size_t)32 << 20;
-    static constexpr int SLOTS = 3;
-    void *pinned[SLOTS] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev[SLOTS] = {nullptr, nullptr, nullptr};
-    bool busy[SLOTS] = {false, false, false};
-    bool ensure() {
+    static constexpr int SLOTS = 4;
+    void *pinned[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    bool busy[SLOTS] = {false, false, false, false};
+    int slot = 0;                            // next slot to fill
+    // worker pool: one job at a time, cut into pieces that the workers and the calling thread pull
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    char *job_dst = nullptr;
+    const char *job_src = nullptr;
+    size_t job_n = 0, job_piece = 0, job_pieces = 0, next_piece = 0, pieces_done = 0;
+    unsigned long long generation = 0;
+    bool stop = false;
+
+    static int default_threads() {
+        static const int env = [] { const char *v = getenv("AM_STAGE_THREADS"); return v && *v ? atoi(v) : -1; }();
+        if (env >= 0) return env;
+        const int hw = (int)std::thread::hardware_concurrency();
+        return std::max(1, std::min(12, hw / 2));
+    }
+    bool ensure(int threads) {
         for (int i = 0; i < SLOTS; ++i) {
             if (!pinned[i] && cudaHostAlloc(&pinned[i], CHUNK, cudaHostAllocDefault) != cudaSuccess) { pinned[i] = nullptr; cudaGetLastError(); return false; }
             if (!ev[i] && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { ev[i] = nullptr; cudaGetLastError(); return false; }
         }
+        while ((int)workers.size() + 1 < threads) workers.emplace_back([this] { work(); });
         return true;
     }
-    static void parallel_copy(void *dst, const void *src, size_t n, int threads) {
-        if (threads <= 1 || n < ((size_t)4 << 20)) { memcpy(dst, src, n); return; }
-        const size_t per = ((n / threads + 4095) / 4096) * 4096;
-        std::vector<std::thread> pool;
-        for (int t = 1; t < threads; ++t) {
-            const size_t o = per * t;
-            if (o >= n) break;
-            pool.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, std::min(per, n - o)); });
-        }
-        memcpy(dst, src, std::min(per, n));
-        for (auto &th : pool) th.join();
+    bool take_piece(size_t &i) {            // mu held
+        if (next_piece >= job_pieces) return false;
+        i = next_piece++;
+        return true;
     }
-    cudaError_t upload(void *dst_dev, const void *src, size_t bytes, cudaStream_t s, int threads) {
-        int slot = 0;
+    void copy_piece(size_t i) {
+        const size_t o = i * job_piece;
+        memcpy(job_dst + o, job_src + o, std::min(job_piece, job_n - o));
+    }
+    void work() {
+        std::unique_lock<std::mutex> lk(mu);
+        unsigned long long seen = 0;
+        for (;;) {
+            cv_work.wait(lk, [&] { return stop || (generation != seen && next_piece < job_pieces); });
+            if (stop) return;
+            seen = generation;
+            size_t i;
+            while (take_piece(i)) {
+                lk.unlock();
+                copy_piece(i);
+                lk.lock();
+                if (++pieces_done == job_pieces) cv_done.notify_all();
+            }
+        }
+    }
+    void parallel_copy(void *dst, const void *src, size_t n) {
+        if (workers.empty() || n < ((size_t)2 << 20)) { memcpy(dst, src, n); return; }
+        std::unique_lock<std::mutex> lk(mu);
+        job_dst = (char *)dst; job_src = (const char *)src; job_n = n;
+        job_piece = (size_t)1 << 20;
+        job_pieces = (n + job_piece - 1) / job_piece;
+        next_piece = 0; pieces_done = 0;
+        ++generation;
+        cv_work.notify_all();
+        size_t i;
+        while (take_piece(i)) {
+            lk.unlock();
+            copy_piece(i);
+            lk.lock();
+            ++pieces_done;
+        }
+        cv_done.wait(lk, [&] { return pieces_done == job_pieces; });
+    }
+    // wait until the slot's previous asynchronous copy has left it
+    cudaError_t acquire(int sl) {
+        if (busy[sl]) {
+            cudaError_t e = cudaEventSynchronize(ev[sl]);
+            if (e != cudaSuccess) return e;
+            busy[sl] = false;
+        }
+        return cudaSuccess;
+    }
+    cudaError_t send(int sl, void *dst_dev, size_t n, cudaStream_t s) {
+        cudaError_t e = cudaMemcpyAsync(dst_dev, pinned[sl], n, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaEventRecord(ev[sl], s)) != cudaSuccess) return e;
+        busy[sl] = true;
+        return cudaSuccess;
+    }
+    cudaError_t upload(void *dst_dev, const void *src, size_t bytes, cudaStream_t s) {
         for (size_t o = 0; o < bytes; o += CHUNK, slot = (slot + 1) % SLOTS) {
             const size_t n = std::min(CHUNK, bytes - o);
             cudaError_t e;
-            if (busy[slot] && (e = cudaEventSynchronize(ev[slot])) != cudaSuccess) return e;
-            parallel_copy(pinned[slot], (const char *)src + o, n, threads);
-            if ((e = cudaMemcpyAsync((char *)dst_dev + o, pinned[slot], n, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
-            if ((e = cudaEventRecord(ev[slot], s)) != cudaSuccess) return e;
-            busy[slot] = true;
+            if ((e = acquire(slot)) != cudaSuccess) return e;
+            parallel_copy(pinned[slot], (const char *)src + o, n);
+            if ((e = send(slot, (char *)dst_dev + o, n, s)) != cudaSuccess) return e;
         }
         return cudaSuccess;
     }
     void release() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &t : workers) t.join();
+        workers.clear();
+        stop = false;
         for (int i = 0; i < SLOTS; ++i) {
             if (ev[i]) { if (busy[i]) cudaEventSynchronize(ev[i]); cudaEventDestroy(ev[i]); ev[i] = nullptr; }
             if (pinned[i]) { cudaFreeHost(pinned[i]); pinned[i] = nullptr; }
@@ -159,12 +232,14 @@ struct am_matcher {
     std::map<int, float2 *> spectra;         // log2n -> [S][N] conjugate spectra
     DevBuf<float2> d_A, d_B;
     DevBuf<float> d_c, d_tmin, d_tmax;
-    DevBuf<float2> d_rsum;                   // summary mode: {min, max} and {first, last} per aligned run of 16 outputs (two arrays)
+    DevBuf<float4> d_rsum;                   // summary mode: one {min, max, first, last} record per aligned run of 16 outputs
     DevBuf<amp::DevPeak> d_peaks;
+    DevBuf<unsigned char> d_redo;           // summary mode: chunks marked for the dense repeat, [snippet][chunk of the call]
     DevBuf<unsigned long long> d_count;   // [0] = count, [1] low 32 bits = flags
     DevBuf<unsigned char> d_stage[2];
     HostStager stager;                      // pageable host streams only
     DevBuf<unsigned char> d_gsend, d_grecv; // multi-GPU: fixed-size peak records for the all-gather
+    bool in_session = false;                // a push session (am_stream_begin) owns the calc_chunks buffers
     am_progress_fn progress = nullptr;      // optional, fired from the calling thread
     void *progress_user = nullptr;
     am_stats stats;
@@ -393,8 +468,10 @@ bool col_inv_writes_runs(int l1) {
     return false;
 }
 
+// nsn > 1 (ROW_INVERSE only): nsn snippets in one launch of the persistent kernel, see k_row32_stream
 template <int L2, int MODE>
-am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, int l1, int rows) {
+am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, int l1, int rows, int nsn = 1,
+                       size_t spec_stride = 0, size_t b_stride = 0) {
     typedef amk::RowCfg<L2> Cfg;
     static const int ept = [] { const char *v = getenv("AM_ROW_EPT"); return v && *v ? atoi(v) : 32; }();
     if constexpr (L2 == 13 || L2 == 12 || L2 == 14) {
@@ -419,27 +496,43 @@ am_status launch_row_t(am_matcher *h, float2 *A, const float2 *spec, float2 *B, 
                     TRY(set_smem(amk::k_row32_stream<L2, MODE>, C32::SMEM));
                     TRY(h->d_sched.reserve(1));
                     CU(cudaMemsetAsync(h->d_sched.p, 0, sizeof(int), h->stream));
-                    LAUNCH(h, AM_K_ROW, amk::k_row32_stream<L2, MODE><<<rows < ctas ? rows : ctas, C32::THREADS, C32::SMEM, h->stream>>>(A, spec, B, l1, rows, h->d_tw.p, h->d_sched.p));
+                    const long long tickets = (long long)rows * nsn;
+                    LAUNCH(h, AM_K_ROW, amk::k_row32_stream<L2, MODE><<<(unsigned)(tickets < ctas ? tickets : ctas), C32::THREADS, C32::SMEM, h->stream>>>(
+                                            A, spec, B, l1, rows, h->d_tw.p, h->d_sched.p, nsn, spec_stride, b_stride));
                     return AM_OK;
                 }
             }
+            if (nsn > 1) return fail(AM_ERR_UNSUPPORTED, "multi-snippet row launch needs the persistent row kernel");
             TRY(set_smem(amk::k_row32<L2, MODE>, C32::SMEM));
             LAUNCH(h, AM_K_ROW, amk::k_row32<L2, MODE><<<rows, C32::THREADS, C32::SMEM, h->stream>>>(A, spec, B, l1, rows, h->d_tw.p));
             return AM_OK;
         }
     }
+    if (nsn > 1) return fail(AM_ERR_UNSUPPORTED, "multi-snippet row launch needs the persistent row kernel");
     TRY(set_smem(amk::k_row<L2, MODE>, Cfg::SMEM));
     int grid = (rows + Cfg::G - 1) / Cfg::G;
     LAUNCH(h, AM_K_ROW, amk::k_row<L2, MODE><<<grid, Cfg::THREADS, Cfg::SMEM, h->stream>>>(A, spec, B, l1, rows, h->d_tw.p));
     return AM_OK;
 }
-template <int MODE> am_status launch_row(am_matcher *h, int l2, float2 *A, const float2 *spec, float2 *B, int l1, int rows) {
+template <int MODE> am_status launch_row(am_matcher *h, int l2, float2 *A, const float2 *spec, float2 *B, int l1, int rows,
+                                         int nsn = 1, size_t spec_stride = 0, size_t b_stride = 0) {
     switch (l2) {
-#define C_(L) case L: return launch_row_t<L, MODE>(h, A, spec, B, l1, rows);
+#define C_(L) case L: return launch_row_t<L, MODE>(h, A, spec, B, l1, rows, nsn, spec_stride, b_stride);
         C_(10) C_(11) C_(12) C_(13) C_(14)
 #undef C_
     }
     return fail(AM_ERR_UNSUPPORTED, "row length 2^%d not built", l2);
+}
+
+// snippets per inverse-row launch in batch mode: the persistent kernel exists for 8192-point rows with 32 elements
+// per thread; AM_BATCH_SNIPPETS overrides (1 = one launch per snippet)
+int batch_snippets_per_launch(int l2, size_t ns) {
+    // measured on cfg 3 (64 snippets vs 24 h): 1 -> 23.6, 4 -> 25.1, 8 -> 25.0, 16 -> 25.9 stream-h/s
+    static const int env = [] { const char *v = getenv("AM_BATCH_SNIPPETS"); return v && *v ? atoi(v) : 16; }();
+    static const int row_stream = [] { const char *v = getenv("AM_ROW_STREAM"); return v && *v ? atoi(v) : -1; }();
+    static const int row_ept = [] { const char *v = getenv("AM_ROW_EPT"); return v && *v ? atoi(v) : 32; }();
+    if (l2 != 13 || row_stream == 0 || row_ept != 32 || env < 1) return 1;
+    return (int)std::min<size_t>((size_t)env, ns);
 }
 
 // ---- planning -----------------------------------------------------------------------
@@ -489,14 +582,20 @@ amk::StreamView snippet_view(const am_matcher *h, size_t snippet = 0) {
 }
 
 am_status ensure_workspace(am_matcher *h, int log2n, unsigned long long pairs_total, unsigned long long &pairs_per_group) {
-    // launch groups of 64 block pairs at N = 2^22: larger groups amortise the launch tails (24.45 -> 24.05 ms per 24 h)
-    size_t budget = env_mb("AM_WORKSPACE_MB", 2048) << 20;
+    // launch groups of 256 block pairs at N = 2^22 (8 GB): larger groups amortise the launch tails and gaps (64 pairs
+    // 22.8, 128 pairs 22.5, 256 pairs 22.2 ms per 24 h); a batch keeps 2 GB groups, its second workspace holds
+    // several snippets per group
+    size_t budget = env_mb("AM_WORKSPACE_MB", h->S > 1 ? 2048 : 8192) << 20;
     size_t per_pair = sizeof(float2) << log2n;
     unsigned long long g = std::max<size_t>(1, budget / per_pair);
     g = std::min<unsigned long long>(g, pairs_total);
     g = std::min<unsigned long long>(g, 32768);
     TRY(h->d_A.reserve((size_t)g << log2n));
-    if (h->S > 1) TRY(h->d_B.reserve((size_t)g << log2n));
+    if (h->S > 1) {
+        int l1, l2;
+        split(log2n, l1, l2);
+        TRY(h->d_B.reserve(((size_t)g << log2n) * (size_t)batch_snippets_per_launch(l2, h->S)));
+    }
     pairs_per_group = g;
     return AM_OK;
 }
@@ -543,7 +642,7 @@ am_status get_spectrum(am_matcher *h, int log2n, float2 **out) {
 // With several snippets the stream-side work (column pass + forward row pass) is done once per block
 // group and only the multiply + inverse passes run per snippet.
 am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0, long long g1, int log2n, int scale,
-                          float *c, size_t c_stride, long long c_g0, size_t s0, size_t ns, amp::RunRecs rsum = amp::RunRecs{nullptr, nullptr},
+                          float *c, size_t c_stride, long long c_g0, size_t s0, size_t ns, amp::RunRecs rsum = amp::RunRecs{nullptr},
                           float theta = 0.f) {
     if (g1 <= g0 || ns == 0) return AM_OK;
     const float inv_n = (float)(1.0 / (double)(1ull << log2n));
@@ -591,11 +690,18 @@ am_status run_correlation(am_matcher *h, const amk::StreamView &sv, long long g0
         } else {
             TRY(launch_col<false>(h, l1, g, l2, h->d_A.p));
             TRY(launch_row<amk::ROW_FORWARD>(h, l2, h->d_A.p, nullptr, nullptr, l1, rows));
-            for (size_t j = 0; j < ns; ++j) {
-                g.c = c + j * c_stride; g.scalar = scalar_of(s0 + j);
-                if (rsum.mm) g.rsum = rsum.offset((long long)(j * (c_stride >> 4)));
-                TRY(launch_row<amk::ROW_INVERSE>(h, l2, h->d_A.p, spec_all + (s0 + j) * (size_t)N, h->d_B.p, l1, rows));
-                TRY(launch_col<true>(h, l1, g, l2, h->d_B.p));
+            // multiply + inverse rows for sb snippets per launch (the forward rows come from DRAM once per sb
+            // snippets instead of once per snippet), then the inverse column pass per snippet
+            const size_t sb = (size_t)batch_snippets_per_launch(l2, ns), b_stride = (size_t)ppg << log2n;
+            for (size_t j0 = 0; j0 < ns; j0 += sb) {
+                const size_t nj = std::min(sb, ns - j0);
+                TRY(launch_row<amk::ROW_INVERSE>(h, l2, h->d_A.p, spec_all + (s0 + j0) * (size_t)N, h->d_B.p, l1, rows, (int)nj,
+                                                 (size_t)N, b_stride));
+                for (size_t j = j0; j < j0 + nj; ++j) {
+                    g.c = c + j * c_stride; g.scalar = scalar_of(s0 + j);
+                    if (rsum.rec) g.rsum = rsum.offset((long long)(j * (c_stride >> 4)));
+                    TRY(launch_col<true>(h, l1, g, l2, h->d_B.p + (j - j0) * b_stride));
+                }
             }
         }
     }
@@ -775,7 +881,7 @@ void am_matcher_destroy(am_matcher *h) {
     cudaDeviceSynchronize();
     for (auto &kv : h->spectra) cudaFree(kv.second);
     h->d_snip.release(); h->d_tw.release(); h->d_A.release(); h->d_B.release(); h->d_c.release(); h->d_tmin.release();
-    h->d_tmax.release(); h->d_rsum.release(); h->d_peaks.release(); h->d_count.release(); h->d_sched.release();
+    h->d_tmax.release(); h->d_rsum.release(); h->d_peaks.release(); h->d_redo.release(); h->d_count.release(); h->d_sched.release();
     h->d_stage[0].release(); h->d_stage[1].release(); h->stager.release(); h->d_gsend.release(); h->d_grecv.release();
     for (int i = 0; i < 2; ++i) {
         if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
@@ -853,6 +959,7 @@ am_status am_correlate(am_matcher *h, const void *within, size_t n, am_sample_fm
     if (!h || !out_len) return fail(AM_ERR_INVALID, "NULL argument");
     if ((int)fmt < 0 || (int)fmt > 2 || (int)mode < 0 || (int)mode > 2) return fail(AM_ERR_INVALID, "bad fmt/mode");
     std::lock_guard<std::mutex> lk(h->mu);
+    if (h->in_session) return fail(AM_ERR_INVALID, "a push session is open on this matcher");
     CU(cudaSetDevice(h->device));
     memset(&h->stats, 0, sizeof h->stats);
     const size_t olen = am_out_len(n, h->m, mode);
@@ -957,13 +1064,36 @@ am_status am_merge_peaks(am_peak *peaks, size_t n, uint32_t sr, double distance_
     return AM_OK;
 }
 
-// The per-rank part of calc_chunks: correlation + per-chunk peak kernels for logical chunks
-// [first_chunk, first_chunk + num_chunks).  The peaks stay in h->d_peaks (unordered), *count_out of them.
-// The caller holds h->mu.
-static am_status range_pass_device(am_matcher *h, const void *stream, size_t buf_first_frame, size_t buf_frames,
-                                   size_t total_frames, am_sample_fmt fmt, am_mem mem, int scale, size_t first_chunk,
-                                   size_t num_chunks, unsigned long long *count_out) {
-    *count_out = 0;
+// ---- calc_chunks on the device -----------------------------------------------------------------------
+// RangePlan: geometry, buffers and kernel parameters of one calc_chunks call over logical chunks
+// [c_first, c_last) of a stream of L frames.  plan_range() sizes everything, compute_segment() launches the
+// transforms + peak kernels of one segment whose frames are resident on the device, finish_range() collects the
+// counters and repeats marked chunks densely.  The one-shot entry points and the push session share them.
+struct RangePlan {
+    long long C = 0, ov = 0, L = 0, m = 0, c_first = 0, c_last = 0, K = 1, seg_c_len = 0, tiles_stride = 0;
+    size_t S = 1, fb = 2, pk_smem = 0, dev_cap = 0, num_chunks = 0;
+    int log2n = 0, pk_cap = 1024, sm_tiles = 0, scale = 1, fmt = 0;
+    bool summary = false;
+    unsigned long long min_dist = 0;
+    float theta = 0.f;
+    amp::PeakOut po;
+    amp::RunRecs recs{nullptr};
+    long long chunk_end(long long i) const {                 // one past the last global offset chunk i evaluates
+        long long n = std::min(C + ov, L - C * i);
+        return n >= m ? C * i + n - m + 1 : C * i;
+    }
+    long long seg_out_end(long long i0, long long i1) const {   // one past the last output of chunks [i0, i1); C i0 if none
+        for (long long i = i1 - 1; i >= i0; --i)
+            if (chunk_end(i) > C * i) return chunk_end(i);
+        return C * i0;
+    }
+};
+
+// `mem_host`: host streams take 512 MB segments (a segment is also the unit of the double-buffered upload and the
+// first one is not overlapped with compute), resident streams 4 GB.
+static am_status plan_range(am_matcher *h, size_t total_frames, am_sample_fmt fmt, bool mem_host, int scale, size_t first_chunk,
+                            size_t num_chunks, RangePlan &pl, bool *nothing_to_do) {
+    *nothing_to_do = true;
     if ((int)fmt < 0 || (int)fmt > 2) return fail(AM_ERR_INVALID, "bad sample format");
     CU(cudaSetDevice(h->device));
     memset(&h->stats, 0, sizeof h->stats);
@@ -975,45 +1105,35 @@ static am_status range_pass_device(am_matcher *h, const void *stream, size_t buf
     const size_t total_chunks = am_num_chunks(h, total_frames);
     if (first_chunk >= total_chunks || num_chunks == 0) return AM_OK;
     num_chunks = std::min(num_chunks, total_chunks - first_chunk);
-    const long long c_first = (long long)first_chunk, c_last = c_first + (long long)num_chunks;   // [c_first, c_last)
-    // frames the range reads: [C c_first, min(L, C (c_last-1) + C + ov))
-    const long long need_lo = C * c_first, need_hi = std::min(L, C * (c_last - 1) + C + ov);
-    if (!stream || (long long)buf_first_frame > need_lo || (long long)(buf_first_frame + buf_frames) < need_hi)
-        return fail(AM_ERR_INVALID, "stream buffer [%zu, %zu) does not cover frames [%lld, %lld) of chunks [%lld, %lld)",
-                    buf_first_frame, buf_first_frame + buf_frames, need_lo, need_hi, c_first, c_last);
-
-    auto chunk_end = [&](long long i) {                      // one past the last global offset chunk i evaluates
-        long long n = std::min(C + ov, L - C * i);
-        return n >= m ? C * i + n - m + 1 : C * i;
-    };
-    unsigned long long outputs = 0;
-    for (long long i = c_last - 1; i >= c_first; --i)
-        if (chunk_end(i) > C * i) { outputs = (unsigned long long)(chunk_end(i) - C * c_first); break; }
-    if (outputs == 0) return AM_OK;                          // every window shorter than the snippet
-    int log2n;
-    TRY(choose_log2n(h, outputs, log2n));
+    pl.C = C; pl.ov = ov; pl.L = L; pl.m = m; pl.S = h->S; pl.fb = fmt_bytes(fmt); pl.scale = scale; pl.fmt = (int)fmt;
+    pl.c_first = (long long)first_chunk; pl.c_last = pl.c_first + (long long)num_chunks; pl.num_chunks = num_chunks;
+    const long long out_end = pl.seg_out_end(pl.c_first, pl.c_last);
+    if (out_end <= C * pl.c_first) return AM_OK;             // every window shorter than the snippet
+    TRY(choose_log2n(h, (unsigned long long)(out_end - C * pl.c_first), pl.log2n));
 
     // Summary mode: the inverse column kernel writes one {min, max, first, last} record per aligned run of 16
     // outputs and the outputs themselves only where the run maximum reaches theta = prominence / 2; the peak
-    // kernels work from the records.  Needs 16-column tiles, run-aligned chunks and a positive threshold; if a
-    // chunk turns out to violate the bound (min_prom + chunk_min < theta) or has an unsupported partial run the
-    // kernels raise FLAG_NEED_DENSE and the pass is repeated with the dense correlation.
+    // kernels work from the records.  Needs 16-column tiles, run-aligned chunks whose full windows end on a run
+    // boundary or one output after it (V mod 16 <= 1: the usual ov = m gives V = C + 1), and a positive threshold.
+    // A chunk the records cannot decide exactly (a chunk minimum below theta - prominence whose kept peaks do not
+    // cover it, an odd-length window in the middle of a segment) is marked on the device and exactly those chunks
+    // are repeated on a dense correlation afterwards.
     int sp_l1, sp_l2;
-    split(log2n, sp_l1, sp_l2);
-    bool summary = col_inv_writes_runs(sp_l1) && h->m > (size_t)amk::DIRECT_MAX_M && (C % 16) == 0 &&
-                   h->cfg.prominence > 0.f && std::isfinite(h->cfg.prominence);
+    split(pl.log2n, sp_l1, sp_l2);
+    const long long v_full = C + ov >= m ? C + ov - m + 1 : 0;
+    pl.summary = col_inv_writes_runs(sp_l1) && h->m > (size_t)amk::DIRECT_MAX_M && (C % 16) == 0 && (v_full & 15) <= 1 &&
+                 h->cfg.prominence > 0.f && std::isfinite(h->cfg.prominence);
     {
         static const int env = [] { const char *v = getenv("AM_SUMMARY"); return v && *v ? atoi(v) : 1; }();
-        if (!env) summary = false;
+        if (!env) pl.summary = false;
     }
 
     // segments of K logical chunks share one correlation buffer per snippet; a batch keeps at
     // least ~48 M outputs per snippet per segment so that a segment still spans several block pairs
     const size_t S = h->S;
-    // Resident streams take 4 GB segments (~370 chunks: the per-chunk peak kernel fills the GPU, fewer ragged launch
-    // groups; 25.7 -> 24.5 ms per 24 h).  Host streams keep 512 MB segments: a segment is also the unit of the
-    // double-buffered upload and the first one is not overlapped with compute.
-    size_t seg_mb = mem == AM_MEM_HOST ? 512 : 4096;
+    // Resident streams take 16 GB segments (~1480 chunks: the per-chunk peak kernel fills the GPU, fewer ragged launch
+    // groups; 512 MB 25.7, 4 GB 22.8, 8 GB 22.5, 16 GB 22.2 ms per 24 h).
+    size_t seg_mb = mem_host ? 512 : 16384;
     if (S > 1 && !getenv("AM_SEGMENT_MB")) {
         // a batch shares the budget between its S correlation buffers; short segments mean short launch groups
         // (measured 17.2 vs 13.5 us per snippet and block pair in the inverse row pass), so take up to a quarter of
@@ -1023,115 +1143,173 @@ static am_status range_pass_device(am_matcher *h, const void *stream, size_t buf
     }
     size_t seg_floats = (env_mb("AM_SEGMENT_MB", seg_mb) << 20) / sizeof(float) / S;
     if (S > 1) seg_floats = std::max<size_t>(seg_floats, (size_t)48 << 20);
-    long long K = std::max<long long>(1, (long long)(seg_floats / (size_t)C));
-    K = std::min<long long>(K, (long long)num_chunks);
-    const long long seg_c_len = ((K * C + std::max<long long>(ov - m + 1, 0) + 1 + 15) / 16) * 16;   // float4 / run alignment per snippet
-    TRY(h->d_c.reserve((size_t)seg_c_len * S));
-    const size_t seg_runs = ((size_t)seg_c_len * S) >> 4;
-    if (summary) TRY(h->d_rsum.reserve(2 * seg_runs));
-    const amp::RunRecs recs{h->d_rsum.p, h->d_rsum.p ? h->d_rsum.p + seg_runs : nullptr}, no_recs{nullptr, nullptr};
-    const long long tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
-    TRY(h->d_tmin.reserve((size_t)(K * tiles_stride) * S));
-    TRY(h->d_tmax.reserve((size_t)(K * tiles_stride) * S));
-    const int pk_cap = h->cfg.max_peaks_per_chunk ? (int)h->cfg.max_peaks_per_chunk : 1024;
-    size_t pk_smem = (size_t)pk_cap * (2 * sizeof(unsigned) + 4 * sizeof(float) + 1);
-    if (pk_smem > 200 * 1024) return fail(AM_ERR_INVALID, "max_peaks_per_chunk %d too large", pk_cap);
-    int sm_tiles = 0;                                        // tile summaries staged in shared memory when they fit
-    if (pk_smem + (size_t)tiles_stride * 8 <= 96 * 1024) sm_tiles = (int)tiles_stride;
-    pk_smem += (size_t)sm_tiles * 8;
-    TRY(set_smem(amp::k_chunk_peaks<false>, pk_smem));
-    TRY(set_smem(amp::k_chunk_peaks<true>, pk_smem));
-    const size_t dev_cap = std::min<size_t>((size_t)num_chunks * (size_t)pk_cap * S, (size_t)1 << 22);
-    TRY(h->d_peaks.reserve(dev_cap));
-    amp::PeakOut po;
-    po.peaks = h->d_peaks.p; po.cap = dev_cap; po.count = h->d_count.p; po.flags = (unsigned *)(h->d_count.p + 1);
-    const unsigned long long min_dist = (unsigned long long)h->cfg.distance_s * (unsigned long long)h->sr;  // as_secs(), :228
-    const size_t fb = fmt_bytes(fmt);
-    const float theta = 0.5f * h->cfg.prominence;
-    unsigned long long cnt[2] = {0, 0};
+    pl.K = std::max<long long>(1, (long long)(seg_floats / (size_t)C));
+    pl.K = std::min<long long>(pl.K, (long long)num_chunks);
+    pl.seg_c_len = ((pl.K * C + std::max<long long>(ov - m + 1, 0) + 1 + 15) / 16) * 16;   // float4 / run alignment per snippet
+    TRY(h->d_c.reserve((size_t)pl.seg_c_len * S));
+    if (pl.summary) TRY(h->d_rsum.reserve(((size_t)pl.seg_c_len * S) >> 4));
+    pl.recs = amp::RunRecs{h->d_rsum.p};
+    pl.tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
+    TRY(h->d_tmin.reserve((size_t)(pl.K * pl.tiles_stride) * S));
+    TRY(h->d_tmax.reserve((size_t)(pl.K * pl.tiles_stride) * S));
+    pl.pk_cap = h->cfg.max_peaks_per_chunk ? (int)h->cfg.max_peaks_per_chunk : 1024;
+    if (amp::chunk_peaks_smem(pl.pk_cap, 0) > 200 * 1024) return fail(AM_ERR_INVALID, "max_peaks_per_chunk %d too large", pl.pk_cap);
+    pl.sm_tiles = 0;                                         // tile summaries staged in shared memory when they fit
+    if (amp::chunk_peaks_smem(pl.pk_cap, (int)pl.tiles_stride) <= 96 * 1024) pl.sm_tiles = (int)pl.tiles_stride;
+    pl.pk_smem = amp::chunk_peaks_smem(pl.pk_cap, pl.sm_tiles);
+    TRY(set_smem(amp::k_chunk_peaks<false>, pl.pk_smem));
+    TRY(set_smem(amp::k_chunk_peaks<true>, pl.pk_smem));
+    pl.dev_cap = std::min<size_t>((size_t)num_chunks * (size_t)pl.pk_cap * S, (size_t)1 << 22);
+    TRY(h->d_peaks.reserve(pl.dev_cap));
+    TRY(h->d_redo.reserve((size_t)num_chunks * S));
+    pl.po.peaks = h->d_peaks.p; pl.po.cap = pl.dev_cap; pl.po.count = h->d_count.p; pl.po.flags = (unsigned *)(h->d_count.p + 1);
+    pl.po.redo = h->d_redo.p; pl.po.redo_first = pl.c_first; pl.po.redo_stride = (long long)num_chunks;
+    pl.min_dist = (unsigned long long)h->cfg.distance_s * (unsigned long long)h->sr;  // as_secs(), :228
+    pl.theta = 0.5f * h->cfg.prominence;
+    CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
+    if (pl.summary) CU(cudaMemsetAsync(h->d_redo.p, 0, (size_t)num_chunks * S, h->stream));
+    h->stats.summary_mode = pl.summary ? 1 : 0;
+    *nothing_to_do = false;
+    return AM_OK;
+}
 
-    // pageable host stream: copy through our own pinned ring with a few threads (AM_STAGE_THREADS, 0 = leave it to the driver)
+// Transforms + peak kernels of logical chunks [i0, i1) (at most K of them) on h->stream; `sv` must hold frames
+// [C i0, min(L, seg_out_end + m - 1)).  redo: the dense repeat of the chunks the summary pass marked.
+static am_status compute_segment(am_matcher *h, const RangePlan &pl, const amk::StreamView &sv, long long i0, long long i1,
+                                 bool sum, bool redo) {
+    const long long g0 = pl.C * i0, g1 = pl.seg_out_end(i0, i1);
+    if (g1 <= g0) return AM_OK;
+    const amp::RunRecs no_recs{nullptr};
+    TRY(run_correlation(h, sv, g0, g1, pl.log2n, pl.scale, h->d_c.p, (size_t)pl.seg_c_len, g0, 0, pl.S, sum ? pl.recs : no_recs, pl.theta));
+    amp::ChunkGeom cg;
+    cg.C = pl.C; cg.ov = pl.ov; cg.m = pl.m; cg.total = pl.L; cg.first_chunk = i0; cg.c_g0 = g0; cg.tiles_stride = (int)pl.tiles_stride;
+    cg.c_stride = pl.seg_c_len; cg.seg_end = g1 - g0;
+    dim3 tgrid3((unsigned)((pl.tiles_stride + 7) / 8), (unsigned)(i1 - i0), (unsigned)pl.S), pgrid((unsigned)(i1 - i0), (unsigned)pl.S);
+    if (sum) {
+        LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(pl.recs, cg, h->d_tmin.p, h->d_tmax.p, pl.po));
+        LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<true><<<pgrid, 256, pl.pk_smem, h->stream>>>(
+                                        h->d_c.p, pl.recs, pl.theta, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, pl.min_dist,
+                                        pl.pk_cap, pl.sm_tiles, pl.po, 0));
+    } else {
+        LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid3, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p));
+        LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<false><<<pgrid, 256, pl.pk_smem, h->stream>>>(
+                                        h->d_c.p, no_recs, 0.f, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, pl.min_dist,
+                                        pl.pk_cap, pl.sm_tiles, pl.po, redo ? 1 : 0));
+    }
+    return AM_OK;
+}
+
+// Upload frames [f_lo, f_hi) of a host stream into staging buffer b (copy stream; pageable memory through the pinned
+// ring) and make h->stream wait for it.
+static am_status upload_segment(am_matcher *h, const RangePlan &pl, const void *stream, size_t buf_first_frame, int b,
+                                long long f_lo, long long f_hi, int stage_threads, amk::StreamView &sv) {
+    const size_t bytes = (size_t)(f_hi - f_lo) * pl.fb;
+    CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // kernels that read this buffer are done
+    TRY(h->d_stage[b].reserve(bytes));
+    const unsigned char *src = (const unsigned char *)stream + (size_t)(f_lo - (long long)buf_first_frame) * pl.fb;
+    if (stage_threads > 0 && bytes >= ((size_t)64 << 20) && h->stager.ensure(stage_threads))
+        CU(h->stager.upload(h->d_stage[b].p, src, bytes, h->copy_stream));
+    else
+        CU(cudaMemcpyAsync(h->d_stage[b].p, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CU(cudaEventRecord(h->ev_up[b], h->copy_stream));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_up[b], 0));
+    h->stats.h2d_bytes += bytes;
+    sv.x = h->d_stage[b].p; sv.buf_first = f_lo; sv.buf_frames = f_hi - f_lo;
+    return AM_OK;
+}
+
+// chunks (relative to c_first) the summary pass marked in [r0, r1), any snippet
+static am_status marked_chunks(am_matcher *h, const RangePlan &pl, long long r0, long long r1, std::vector<unsigned char> &any) {
+    any.assign((size_t)(r1 - r0), 0);
+    std::vector<unsigned char> redo((size_t)(r1 - r0));
+    for (size_t sn = 0; sn < pl.S; ++sn) {
+        CU(cudaMemcpy(redo.data(), h->d_redo.p + sn * pl.num_chunks + (size_t)r0, redo.size(), cudaMemcpyDeviceToHost));
+        h->stats.d2h_bytes += redo.size();
+        for (size_t i = 0; i < redo.size(); ++i) any[i] |= redo[i];
+    }
+    return AM_OK;
+}
+
+static am_status fetch_counters(am_matcher *h, unsigned long long (&cnt)[2]) {
+    CU(cudaMemcpyAsync(cnt, h->d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->stats.d2h_bytes += sizeof cnt;
+    return AM_OK;
+}
+
+static am_status check_counters(am_matcher *h, const RangePlan &pl, const unsigned long long (&cnt)[2], unsigned long long *count_out) {
+    if ((unsigned)cnt[1] & amp::FLAG_OVERFLOW)
+        return fail(AM_ERR_CAPACITY, "a chunk kept more than max_peaks_per_chunk = %d peaks, or holds more than that many local maxima of "
+                                     "exactly equal height (raise it, the prominence or the distance)", pl.pk_cap);
+    if (cnt[0] > pl.dev_cap) return fail(AM_ERR_CAPACITY, "%llu peaks exceed the device list capacity %zu", cnt[0], pl.dev_cap);
+    *count_out = cnt[0];
+    return AM_OK;
+}
+
+// The per-rank part of calc_chunks: correlation + per-chunk peak kernels for logical chunks
+// [first_chunk, first_chunk + num_chunks).  The peaks stay in h->d_peaks (unordered), *count_out of them.
+// The caller holds h->mu.
+static am_status range_pass_device(am_matcher *h, const void *stream, size_t buf_first_frame, size_t buf_frames,
+                                   size_t total_frames, am_sample_fmt fmt, am_mem mem, int scale, size_t first_chunk,
+                                   size_t num_chunks, unsigned long long *count_out) {
+    *count_out = 0;
+    RangePlan pl;
+    bool nothing = true;
+    TRY(plan_range(h, total_frames, fmt, mem == AM_MEM_HOST, scale, first_chunk, num_chunks, pl, &nothing));
+    if (nothing) return AM_OK;
+    // frames the range reads: [C c_first, min(L, C (c_last-1) + C + ov))
+    const long long need_lo = pl.C * pl.c_first, need_hi = std::min(pl.L, pl.C * pl.c_last + pl.ov);
+    if (!stream || (long long)buf_first_frame > need_lo || (long long)(buf_first_frame + buf_frames) < need_hi)
+        return fail(AM_ERR_INVALID, "stream buffer [%zu, %zu) does not cover frames [%lld, %lld) of chunks [%lld, %lld)",
+                    buf_first_frame, buf_first_frame + buf_frames, need_lo, need_hi, pl.c_first, pl.c_last);
+
+    // pageable host stream: copy through our own pinned ring with a pool of threads (AM_STAGE_THREADS, 0 = leave it to the driver)
     int stage_threads = 0;
     if (mem == AM_MEM_HOST) {
         cudaPointerAttributes pa;
-        if (cudaPointerGetAttributes(&pa, stream) == cudaSuccess && pa.type == cudaMemoryTypeUnregistered) {
-            static const int env = [] { const char *v = getenv("AM_STAGE_THREADS"); return v && *v ? atoi(v) : -1; }();
-            const int hw = (int)std::thread::hardware_concurrency();
-            stage_threads = env >= 0 ? env : std::max(1, std::min(8, hw / 4));
-        }
+        if (cudaPointerGetAttributes(&pa, stream) == cudaSuccess && pa.type == cudaMemoryTypeUnregistered) stage_threads = HostStager::default_threads();
         cudaGetLastError();
     }
-
-    // one pass over all segments: transforms + peak kernels; the counters come back in cnt
-    auto run_pass = [&](bool sum) -> am_status {
-        CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
-        int seg_idx = 0;
-        for (long long i0 = c_first; i0 < c_last; i0 += K, ++seg_idx) {
-            const long long i1 = std::min(c_last, i0 + K);
-            const long long g0 = C * i0;
-            long long g1 = g0;
-            for (long long i = i1 - 1; i >= i0; --i)
-                if (chunk_end(i) > C * i) { g1 = chunk_end(i); break; }
-            if (g1 <= g0) continue;
-            amk::StreamView sv;
-            sv.fmt = (int)fmt; sv.total = L; sv.lead = 0;
-            if (mem == AM_MEM_HOST) {
-                const int b = seg_idx & 1;
-                const long long f_lo = g0, f_hi = std::min(L, g1 + m - 1);
-                const size_t bytes = (size_t)(f_hi - f_lo) * fb;
-                CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // kernels that read this buffer are done
-                TRY(h->d_stage[b].reserve(bytes));
-                const unsigned char *src = (const unsigned char *)stream + (size_t)(f_lo - (long long)buf_first_frame) * fb;
-                if (stage_threads > 0 && bytes >= ((size_t)64 << 20) && h->stager.ensure())
-                    CU(h->stager.upload(h->d_stage[b].p, src, bytes, h->copy_stream, stage_threads));
-                else
-                    CU(cudaMemcpyAsync(h->d_stage[b].p, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
-                CU(cudaEventRecord(h->ev_up[b], h->copy_stream));
-                CU(cudaStreamWaitEvent(h->stream, h->ev_up[b], 0));
-                h->stats.h2d_bytes += bytes;
-                sv.x = h->d_stage[b].p; sv.buf_first = f_lo; sv.buf_frames = f_hi - f_lo;
-            } else {
-                sv.x = stream; sv.buf_first = (long long)buf_first_frame; sv.buf_frames = (long long)buf_frames;
-            }
-            TRY(run_correlation(h, sv, g0, g1, log2n, scale, h->d_c.p, (size_t)seg_c_len, g0, 0, S,
-                                sum ? recs : no_recs, theta));
-            if (mem == AM_MEM_HOST) CU(cudaEventRecord(h->ev_done[seg_idx & 1], h->stream));
-            if (h->progress) h->progress(h->progress_user, 0, (size_t)i0, (size_t)(i1 - i0));
-            amp::ChunkGeom cg;
-            cg.C = C; cg.ov = ov; cg.m = m; cg.total = L; cg.first_chunk = i0; cg.c_g0 = g0; cg.tiles_stride = (int)tiles_stride;
-            cg.c_stride = seg_c_len; cg.seg_end = g1 - g0;
-            dim3 tgrid3((unsigned)((tiles_stride + 7) / 8), (unsigned)(i1 - i0), (unsigned)S), pgrid((unsigned)(i1 - i0), (unsigned)S);
-            if (sum) {
-                LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(recs, cg, h->d_tmin.p, h->d_tmax.p, po.flags));
-                LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<true><<<pgrid, 256, pk_smem, h->stream>>>(
-                                                h->d_c.p, recs, theta, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist,
-                                                pk_cap, sm_tiles, po));
-            } else {
-                LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_minmax<<<tgrid3, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p));
-                LAUNCH(h, AM_K_CHUNK_PEAKS, amp::k_chunk_peaks<false><<<pgrid, 256, pk_smem, h->stream>>>(
-                                                h->d_c.p, no_recs, 0.f, cg, h->d_tmin.p, h->d_tmax.p, h->cfg.prominence, min_dist,
-                                                pk_cap, sm_tiles, po));
-            }
+    int seg_idx = 0;
+    auto run_segment = [&](long long i0, long long i1, bool sum, bool redo) -> am_status {
+        const long long g0 = pl.C * i0, g1 = pl.seg_out_end(i0, i1);
+        if (g1 <= g0) return AM_OK;
+        amk::StreamView sv;
+        sv.fmt = (int)fmt; sv.total = pl.L; sv.lead = 0;
+        if (mem == AM_MEM_HOST) {
+            TRY(upload_segment(h, pl, stream, buf_first_frame, seg_idx & 1, g0, std::min(pl.L, g1 + pl.m - 1), stage_threads, sv));
+        } else {
+            sv.x = stream; sv.buf_first = (long long)buf_first_frame; sv.buf_frames = (long long)buf_frames;
         }
-        CU(cudaMemcpyAsync(cnt, h->d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        h->stats.d2h_bytes += sizeof cnt;
+        TRY(compute_segment(h, pl, sv, i0, i1, sum, redo));
+        if (mem == AM_MEM_HOST) CU(cudaEventRecord(h->ev_done[seg_idx & 1], h->stream));
+        ++seg_idx;
+        if (h->progress && !redo) h->progress(h->progress_user, 0, (size_t)i0, (size_t)(i1 - i0));
         return AM_OK;
     };
-    TRY(run_pass(summary));
-    h->stats.summary_mode = summary ? 1 : 0;
-    if (summary && ((unsigned)cnt[1] & amp::FLAG_NEED_DENSE)) {
-        h->stats.summary_mode = 2;                           // summary pass rejected, repeated densely
-        TRY(run_pass(false));
+    unsigned long long cnt[2] = {0, 0};
+    for (long long i0 = pl.c_first; i0 < pl.c_last; i0 += pl.K) TRY(run_segment(i0, std::min(pl.c_last, i0 + pl.K), pl.summary, false));
+    TRY(fetch_counters(h, cnt));
+    if (pl.summary && ((unsigned)cnt[1] & amp::FLAG_NEED_DENSE) && !((unsigned)cnt[1] & amp::FLAG_OVERFLOW)) {
+        // dense repeat of exactly the marked chunks: consecutive marked chunks share a segment
+        std::vector<unsigned char> any;
+        TRY(marked_chunks(h, pl, 0, (long long)pl.num_chunks, any));
+        h->stats.summary_mode = 2;
+        for (long long i = 0; i < (long long)pl.num_chunks;) {
+            if (!any[(size_t)i]) { ++i; continue; }
+            long long j = i;
+            while (j < (long long)pl.num_chunks && any[(size_t)j] && j - i < pl.K) ++j;
+            h->stats.dense_chunks += (uint32_t)(j - i);
+            TRY(run_segment(pl.c_first + i, pl.c_first + j, false, true));
+            i = j;
+        }
+        TRY(fetch_counters(h, cnt));
     }
     prof_collect(h);
     h->stats.frames = (uint64_t)(need_hi - need_lo);
-    h->stats.chunks = (uint32_t)num_chunks;
-    if ((unsigned)cnt[1] & 1u)
-        return fail(AM_ERR_CAPACITY, "a chunk produced more than max_peaks_per_chunk = %d peak candidates (raise it or the prominence)", pk_cap);
-    if (cnt[0] > dev_cap) return fail(AM_ERR_CAPACITY, "%llu peaks exceed the device list capacity %zu", cnt[0], dev_cap);
-    *count_out = cnt[0];
-    if (h->progress) h->progress(h->progress_user, 1, first_chunk, num_chunks);
+    h->stats.chunks = (uint32_t)pl.num_chunks;
+    TRY(check_counters(h, pl, cnt, count_out));
+    if (h->progress) h->progress(h->progress_user, 1, first_chunk, pl.num_chunks);
     return AM_OK;
 }
 
@@ -1141,6 +1319,7 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
     if (!h || !n_out) return fail(AM_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     *n_out = 0;
+    if (h->in_session) return fail(AM_ERR_INVALID, "a push session is open on this matcher");
     unsigned long long count = 0;
     TRY(range_pass_device(h, stream, buf_first_frame, buf_frames, total_frames, fmt, mem, scale, first_chunk, num_chunks, &count));
     std::vector<am_peak> all((size_t)count);
@@ -1175,6 +1354,233 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
 }
 
 
+// ---- push session: calc_chunks for a decoder that produces the stream piece by piece -------------------
+// The reference feeds calc_chunks a lazy iterator of decoded frames (mp3_reader.rs:13-66, matcher/mod.rs:71-83).
+// Here the decoder thread pushes whatever it has; frames collect in the pinned ring (one asynchronous copy per
+// 32 MB, or per segment end) and land in one of two device segment buffers.  As soon as the frames of a segment of
+// K logical chunks are complete its transforms + peak kernels are launched, so matching overlaps decoding and the
+// uploads; only the last, partial segment is left for am_stream_finish.
+struct am_stream_session {
+    am_matcher *h = nullptr;
+    RangePlan pl;
+    long long max_frames = 0, pushed = 0;
+    long long seg_i0 = 0;            // first logical chunk of the segment being filled
+    int b = 0;                       // device staging buffer of that segment
+    long long seg_cap = 0;           // frames of a full segment: K C + ov
+    int slot = -1;                   // pinned slot being filled, -1 = none
+    size_t slot_fill = 0;            // bytes in it
+    long long slot_first = 0;        // stream frame of its first byte
+    bool have_prev = false;          // the previous launch still awaits its marked-chunk check
+    long long prev_i0 = 0, prev_i1 = 0, prev_origin = 0;   // its chunks, and the first chunk held by its buffer
+    int prev_b = 0;
+    bool failed = false;
+};
+
+namespace {
+am_status session_flush_slot(am_stream_session *s) {
+    am_matcher *h = s->h;
+    if (s->slot < 0 || s->slot_fill == 0) return AM_OK;
+    const long long seg_first = s->pl.C * s->seg_i0;
+    void *dst = h->d_stage[s->b].p + (size_t)(s->slot_first - seg_first) * s->pl.fb;
+    CU(h->stager.send(s->slot, dst, s->slot_fill, h->copy_stream));
+    h->stats.h2d_bytes += s->slot_fill;
+    h->stager.slot = (s->slot + 1) % HostStager::SLOTS;
+    s->slot = -1;
+    s->slot_fill = 0;
+    return AM_OK;
+}
+// device buffer b holds frames [C origin, frames_end)
+amk::StreamView session_view(const am_stream_session *s, int b, long long origin, long long frames_end) {
+    amk::StreamView sv;
+    sv.fmt = s->pl.fmt; sv.total = s->pl.L; sv.lead = 0;
+    sv.x = s->h->d_stage[b].p; sv.buf_first = s->pl.C * origin; sv.buf_frames = frames_end - sv.buf_first;
+    return sv;
+}
+// dense repeat of the chunks of the previous segment that the summary pass marked (its frames are still in prev_b)
+am_status session_settle_prev(am_stream_session *s) {
+    am_matcher *h = s->h;
+    if (!s->have_prev) return AM_OK;
+    s->have_prev = false;
+    if (!s->pl.summary) return AM_OK;
+    unsigned long long cnt[2];
+    TRY(fetch_counters(h, cnt));
+    if (!((unsigned)cnt[1] & amp::FLAG_NEED_DENSE) || ((unsigned)cnt[1] & amp::FLAG_OVERFLOW)) return AM_OK;
+    std::vector<unsigned char> any;
+    TRY(marked_chunks(h, s->pl, s->prev_i0 - s->pl.c_first, s->prev_i1 - s->pl.c_first, any));
+    const long long frames_end = std::min(s->pl.L, s->pl.C * s->prev_i1 + s->pl.ov);
+    for (long long i = 0; i < (long long)any.size();) {
+        if (!any[(size_t)i]) { ++i; continue; }
+        long long j = i;
+        while (j < (long long)any.size() && any[(size_t)j]) ++j;
+        h->stats.summary_mode = 2;
+        h->stats.dense_chunks += (uint32_t)(j - i);
+        TRY(compute_segment(h, s->pl, session_view(s, s->prev_b, s->prev_origin, frames_end), s->prev_i0 + i, s->prev_i0 + j, false, true));
+        i = j;
+    }
+    CU(cudaEventRecord(h->ev_done[s->prev_b], h->stream));
+    return AM_OK;
+}
+// all frames of chunks [i0, i1) (at most K of them, i0 >= seg_i0) are on their way into the current buffer: launch them
+am_status session_launch(am_stream_session *s, long long i0, long long i1, long long frames_end) {
+    am_matcher *h = s->h;
+    TRY(session_flush_slot(s));
+    CU(cudaEventRecord(h->ev_up[s->b], h->copy_stream));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_up[s->b], 0));
+    TRY(session_settle_prev(s));
+    TRY(compute_segment(h, s->pl, session_view(s, s->b, s->seg_i0, frames_end), i0, i1, s->pl.summary, false));
+    CU(cudaEventRecord(h->ev_done[s->b], h->stream));
+    if (h->progress) h->progress(h->progress_user, 0, (size_t)i0, (size_t)(i1 - i0));
+    s->have_prev = true; s->prev_i0 = i0; s->prev_i1 = i1; s->prev_origin = s->seg_i0; s->prev_b = s->b;
+    return AM_OK;
+}
+}  // namespace
+
+am_status am_stream_begin(am_matcher *h, size_t max_frames, am_sample_fmt fmt, int scale, am_stream_session **out) {
+    if (!h || !out) return fail(AM_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (max_frames == 0) return fail(AM_ERR_INVALID, "max_frames is 0 (pass the claimed stream length, mod.rs:78)");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->in_session) return fail(AM_ERR_INVALID, "a push session is already open on this matcher");
+    am_stream_session *s = new (std::nothrow) am_stream_session();
+    if (!s) return fail(AM_ERR_NOMEM, "out of host memory");
+    s->h = h;
+    s->max_frames = (long long)max_frames;
+    bool nothing = true;
+    am_status st = plan_range(h, max_frames, fmt, true, scale, 0, (size_t)-1, s->pl, &nothing);
+    if (st == AM_OK && !nothing) {
+        s->seg_cap = s->pl.K * s->pl.C + s->pl.ov;
+        for (int b = 0; b < 2 && st == AM_OK; ++b) st = h->d_stage[b].reserve((size_t)std::min(s->seg_cap, s->max_frames) * s->pl.fb);
+        if (st == AM_OK && !h->stager.ensure(HostStager::default_threads())) st = fail(AM_ERR_NOMEM, "pinned staging ring");
+    } else if (st == AM_OK) {
+        // the stream cannot hold a single output (shorter than the snippet): accept the frames, report no peaks
+        s->pl.fb = fmt_bytes(fmt);
+        s->seg_cap = 0;
+    }
+    if (st != AM_OK) { delete s; return st; }
+    h->in_session = true;
+    *out = s;
+    return AM_OK;
+}
+
+am_status am_stream_push(am_stream_session *s, const void *pcm, size_t frames) {
+    if (!s) return fail(AM_ERR_INVALID, "NULL session");
+    if (frames == 0) return AM_OK;
+    if (!pcm) return fail(AM_ERR_INVALID, "NULL buffer");
+    am_matcher *h = s->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (s->failed) return fail(AM_ERR_INVALID, "the session has failed; call am_stream_abort");
+    if (s->pushed + (long long)frames > s->max_frames)
+        return fail(AM_ERR_INVALID, "%lld frames pushed, more than the %lld announced to am_stream_begin", s->pushed + (long long)frames, s->max_frames);
+    if (s->seg_cap == 0) { s->pushed += (long long)frames; return AM_OK; }
+    CU(cudaSetDevice(h->device));
+    auto body = [&]() -> am_status {
+        const unsigned char *src = (const unsigned char *)pcm;
+        long long left = (long long)frames;
+        const size_t fb = s->pl.fb;
+        while (left > 0) {
+            const long long seg_first = s->pl.C * s->seg_i0;
+            const long long room = seg_first + s->seg_cap - s->pushed;       // frames until the segment is complete
+            if (s->slot < 0) {
+                s->slot = h->stager.slot;
+                CU(h->stager.acquire(s->slot));
+                if (s->pushed == seg_first + (s->seg_i0 > 0 ? s->pl.ov : 0))   // first upload into this buffer: its previous kernels must be done
+                    CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[s->b], 0));
+                s->slot_fill = 0;
+                s->slot_first = s->pushed;
+            }
+            const long long slot_room = (long long)((HostStager::CHUNK - s->slot_fill) / fb);
+            const long long take = std::min(left, std::min(room, slot_room));
+            h->stager.parallel_copy((char *)h->stager.pinned[s->slot] + s->slot_fill, src, (size_t)take * fb);
+            s->slot_fill += (size_t)take * fb;
+            s->pushed += take;
+            src += (size_t)take * fb;
+            left -= take;
+            if (take == slot_room) TRY(session_flush_slot(s));
+            if (take == room) {
+                // segment complete: launch it, then seed the next buffer with the ov-frame halo (device to device)
+                const long long i1 = s->seg_i0 + s->pl.K;
+                TRY(session_launch(s, s->seg_i0, i1, s->pushed));
+                const int nb = s->b ^ 1;
+                CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[nb], 0));
+                if (s->pl.ov > 0)
+                    CU(cudaMemcpyAsync(h->d_stage[nb].p, h->d_stage[s->b].p + (size_t)(s->pl.K * s->pl.C) * fb, (size_t)s->pl.ov * fb,
+                                       cudaMemcpyDeviceToDevice, h->copy_stream));
+                s->seg_i0 = i1;
+                s->b = nb;
+            }
+        }
+        return AM_OK;
+    };
+    const am_status st = body();
+    if (st != AM_OK) s->failed = true;
+    return st;
+}
+
+static void session_close(am_stream_session *s) {
+    am_matcher *h = s->h;
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < HostStager::SLOTS; ++i) h->stager.busy[i] = false;
+    h->in_session = false;
+    delete s;
+}
+
+void am_stream_abort(am_stream_session *s) {
+    if (!s) return;
+    std::lock_guard<std::mutex> lk(s->h->mu);
+    cudaSetDevice(s->h->device);
+    session_close(s);
+}
+
+am_status am_stream_finish(am_stream_session *s, am_peak *out, size_t cap, size_t *n_out) {
+    if (!s || !n_out) return fail(AM_ERR_INVALID, "NULL argument");
+    am_matcher *h = s->h;
+    std::lock_guard<std::mutex> lk(h->mu);
+    *n_out = 0;
+    auto body = [&]() -> am_status {
+        if (s->failed) return fail(AM_ERR_INVALID, "the session has failed");
+        CU(cudaSetDevice(h->device));
+        if (s->seg_cap == 0) return AM_OK;
+        // the stream's true length is what was pushed (<= the announced maximum): the tail chunks get their real windows
+        RangePlan &pl = s->pl;
+        pl.L = s->pushed;
+        const long long c_last = (long long)am_num_chunks(h, (size_t)s->pushed);
+        unsigned long long cnt[2] = {0, 0};
+        // (a tail that stops just short of a full segment can span a few chunks more than K: ov frames past the last full window)
+        TRY(session_flush_slot(s));
+        for (long long i0 = s->seg_i0; i0 < c_last; i0 += pl.K) TRY(session_launch(s, i0, std::min(c_last, i0 + pl.K), s->pushed));
+        TRY(session_settle_prev(s));
+        TRY(fetch_counters(h, cnt));
+        CU(cudaStreamSynchronize(h->copy_stream));
+        prof_collect(h);
+        h->stats.frames = (uint64_t)s->pushed;
+        h->stats.chunks = (uint32_t)c_last;
+        unsigned long long count = 0;
+        TRY(check_counters(h, pl, cnt, &count));
+        std::vector<am_peak> all((size_t)count), kept((size_t)count);
+        if (count) {
+            CU(cudaMemcpy(all.data(), h->d_peaks.p, (size_t)count * sizeof(am_peak), cudaMemcpyDeviceToHost));
+            h->stats.d2h_bytes += (size_t)count * sizeof(am_peak);
+        }
+        size_t nk = 0;
+        TRY(am_merge_peaks(all.data(), all.size(), h->sr, h->cfg.distance_s, kept.data(), kept.size(), &nk));
+        *n_out = nk;
+        if (nk > cap) return fail(AM_ERR_CAPACITY, "%zu peaks, capacity %zu", nk, cap);
+        if (nk) {
+            if (!out) return fail(AM_ERR_INVALID, "NULL output buffer");
+            memcpy(out, kept.data(), nk * sizeof(am_peak));
+        }
+        if (h->progress) h->progress(h->progress_user, 1, 0, (size_t)c_last);
+        return AM_OK;
+    };
+    const am_status st = body();
+    char msg[sizeof g_err];
+    memcpy(msg, g_err, sizeof g_err);
+    session_close(s);
+    memcpy(g_err, msg, sizeof g_err);
+    return st;
+}
+
 // Test hook (tests/test_gpu_parity.py): run the per-chunk peak kernels on a correlation supplied by the caller
 // instead of one computed from a stream.  `c_host` holds the n outputs of one segment that starts at chunk 0; the
 // chunk geometry comes from the matcher's config and snippet length.  summary != 0 exercises the run-record path
@@ -1192,23 +1598,24 @@ am_status am_debug_peaks_from_correlation(am_matcher *h, const float *c_host, si
     const long long nchunks = (L + C - 1) / C;
     const long long seg_c_len = (((long long)n + 15) / 16) * 16;
     TRY(h->d_c.reserve((size_t)seg_c_len));
-    TRY(h->d_rsum.reserve(2 * ((size_t)seg_c_len >> 4)));
-    const amp::RunRecs recs{h->d_rsum.p, h->d_rsum.p + ((size_t)seg_c_len >> 4)}, no_recs{nullptr, nullptr};
+    TRY(h->d_rsum.reserve((size_t)seg_c_len >> 4));
+    const amp::RunRecs recs{h->d_rsum.p}, no_recs{nullptr};
     const long long tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
     TRY(h->d_tmin.reserve((size_t)(nchunks * tiles_stride)));
     TRY(h->d_tmax.reserve((size_t)(nchunks * tiles_stride)));
     const int pk_cap = h->cfg.max_peaks_per_chunk ? (int)h->cfg.max_peaks_per_chunk : 1024;
-    size_t pk_smem = (size_t)pk_cap * (2 * sizeof(unsigned) + 4 * sizeof(float) + 1);
+    if (amp::chunk_peaks_smem(pk_cap, 0) > 200 * 1024) return fail(AM_ERR_INVALID, "max_peaks_per_chunk too large");
     int sm_tiles = 0;
-    if (pk_smem + (size_t)tiles_stride * 8 <= 96 * 1024) sm_tiles = (int)tiles_stride;
-    pk_smem += (size_t)sm_tiles * 8;
-    if (pk_smem > 200 * 1024) return fail(AM_ERR_INVALID, "max_peaks_per_chunk too large");
+    if (amp::chunk_peaks_smem(pk_cap, (int)tiles_stride) <= 96 * 1024) sm_tiles = (int)tiles_stride;
+    const size_t pk_smem = amp::chunk_peaks_smem(pk_cap, sm_tiles);
     TRY(set_smem(amp::k_chunk_peaks<false>, pk_smem));
     TRY(set_smem(amp::k_chunk_peaks<true>, pk_smem));
     const size_t dev_cap = std::min<size_t>((size_t)nchunks * (size_t)pk_cap, (size_t)1 << 22);
     TRY(h->d_peaks.reserve(dev_cap));
+    TRY(h->d_redo.reserve((size_t)nchunks));
     amp::PeakOut po;
     po.peaks = h->d_peaks.p; po.cap = dev_cap; po.count = h->d_count.p; po.flags = (unsigned *)(h->d_count.p + 1);
+    po.redo = h->d_redo.p; po.redo_first = 0; po.redo_stride = nchunks;
     const unsigned long long min_dist = (unsigned long long)h->cfg.distance_s * (unsigned long long)h->sr;
     const float theta = 0.5f * h->cfg.prominence;
     amp::ChunkGeom cg;
@@ -1217,21 +1624,22 @@ am_status am_debug_peaks_from_correlation(am_matcher *h, const float *c_host, si
     dim3 tgrid3((unsigned)((tiles_stride + 7) / 8), (unsigned)nchunks, 1), pgrid((unsigned)nchunks, 1);
     unsigned long long cnt[2] = {0, 0};
     uint32_t mode = summary ? 1 : 0;
+    CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_redo.p, 0, (size_t)nchunks, h->stream));
     for (int pass = 0; pass < 2; ++pass) {
         const bool sum = summary && pass == 0;
         if (pass == 1 && !(summary && ((unsigned)cnt[1] & amp::FLAG_NEED_DENSE))) break;
-        if (pass == 1) mode = 2;
-        CU(cudaMemsetAsync(h->d_count.p, 0, 2 * sizeof(unsigned long long), h->stream));
+        if (pass == 1) mode = 2;                             // the marked chunks are repeated on the dense correlation
         CU(cudaMemcpyAsync(h->d_c.p, c_host, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         if (sum) {
             amp::k_debug_make_runs<<<(unsigned)(((seg_c_len >> 4) + 255) / 256), 256, 0, h->stream>>>(h->d_c.p, (long long)n, theta, recs);
-            amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(recs, cg, h->d_tmin.p, h->d_tmax.p, po.flags);
+            amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(recs, cg, h->d_tmin.p, h->d_tmax.p, po);
             amp::k_chunk_peaks<true><<<pgrid, 256, pk_smem, h->stream>>>(h->d_c.p, recs, theta, cg, h->d_tmin.p, h->d_tmax.p,
-                                                                       h->cfg.prominence, min_dist, pk_cap, sm_tiles, po);
+                                                                       h->cfg.prominence, min_dist, pk_cap, sm_tiles, po, 0);
         } else {
             amp::k_tile_minmax<<<tgrid3, 256, 0, h->stream>>>(h->d_c.p, cg, h->d_tmin.p, h->d_tmax.p);
             amp::k_chunk_peaks<false><<<pgrid, 256, pk_smem, h->stream>>>(h->d_c.p, no_recs, 0.f, cg, h->d_tmin.p, h->d_tmax.p,
-                                                                        h->cfg.prominence, min_dist, pk_cap, sm_tiles, po);
+                                                                        h->cfg.prominence, min_dist, pk_cap, sm_tiles, po, pass);
         }
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(cnt, h->d_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
@@ -1350,6 +1758,7 @@ am_status am_calc_chunks_sharded(am_matcher *h, am_comm *comm, const void *strea
                                     num_chunks, 1, out, cap, n_out);
     std::lock_guard<std::mutex> lk(h->mu);
     *n_out = 0;
+    if (h->in_session) return fail(AM_ERR_INVALID, "a push session is open on this matcher");
     if (h->device != comm->device) return fail(AM_ERR_INVALID, "matcher lives on device %d, communicator on %d", h->device, comm->device);
     NcclApi &api = nccl_api();
     unsigned long long count = 0;

@@ -85,8 +85,8 @@ struct BlockGroup {
     long long c_g0;
     float scalar;       // 1/N or 1/(N sum s^2)
     // Summary mode (k_col_inv with 16-column tiles only): for every aligned run of 16 outputs the kernel writes
-    // rsum.mm[(g - c_g0) >> 4] = {min, max}, rsum.fl[...] = {first, last} and stores the 16 values themselves only
-    // when max >= theta.  theta = -inf keeps the correlation dense.  mm == nullptr: no records, plain dense stores.
+    // rsum.rec[(g - c_g0) >> 4] = {min, max, first, last} and stores the 16 values themselves only when max >= theta.
+    // theta = -inf keeps the correlation dense.  rec == nullptr: no records, plain dense stores.
     amp::RunRecs rsum;
     float theta;
 };
@@ -503,7 +503,7 @@ k_col_inv(BlockGroup g, int log2n2_arg, const float2 *__restrict__ A, const floa
     I::template run<0, true, false, true>(v, sm_all, tid, tw);
     const long long o0 = g.g0 + (long long)(2 * pair) * g.VN;
     if constexpr (Cfg::LT == 4) {
-        if (g.rsum.mm != nullptr) {
+        if (g.rsum.rec != nullptr) {
             // Summary epilogue: transpose the tile through the (now idle) exchange buffer so that every thread owns
             // whole rows = aligned runs of 16 outputs of both blocks, then write one {min, max, first, last} record
             // per run and the run itself (four 128-bit stores) only if its maximum reaches theta.
@@ -547,8 +547,7 @@ k_col_inv(BlockGroup g, int log2n2_arg, const float2 *__restrict__ A, const floa
                             if (i < valid) { mn = fminf(mn, vals[i]); mx = fmaxf(mx, vals[i]); last = vals[i]; }
                     }
                     const long long ci = o - g.c_g0;
-                    g.rsum.mm[ci >> 4] = make_float2(mn, mx);
-                    g.rsum.fl[ci >> 4] = make_float2(vals[0], last);
+                    g.rsum.rec[ci >> 4] = make_float4(mn, mx, vals[0], last);
                     if (mx >= g.theta) {
                         float *dst = g.c + ci;
                         if (valid == 16) {
@@ -745,10 +744,14 @@ __device__ __forceinline__ void bulk_load(unsigned smem_dst, const void *gsrc, u
 }
 // MODE = ROW_FUSED (in place) or ROW_INVERSE (batch: A holds forward spectra, output to Bout; the spectrum row is an
 // L2 hit thanks to the k1-major order and is read with plain loads while the row of A waits in shared memory).
+// Batch mode (ROW_INVERSE) takes nsn snippets per launch: ticket = (row ticket) * nsn + snippet, so the nsn CTAs that
+// need the same row of A run back to back (one DRAM fetch, the rest are L2 hits) while the k1-major row order keeps
+// the nsn spectrum rows of the current k1 in L2 for all block pairs of the group.  Snippet j reads spec + j * spec_stride
+// and writes Bout + j * b_stride.
 template <int L2, int MODE>
 __global__ void __launch_bounds__(Row32Cfg<L2>::THREADS, 2)
 k_row32_stream(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restrict__ Bout, int log2n1, int rows,
-               const float2 *__restrict__ tw, int *__restrict__ next_row) {
+               const float2 *__restrict__ tw, int *__restrict__ next_row, int nsn, size_t spec_stride, size_t b_stride) {
     typedef RegFFT<L2, 0, false, 32> F;
     typedef RegFFT<L2, 0, true, 32> I;
     static_assert(MODE == ROW_FUSED || MODE == ROW_INVERSE, "fused or inverse-only");
@@ -761,7 +764,8 @@ k_row32_stream(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *
     const unsigned bar_row = (unsigned)__cvta_generic_to_shared(&bar_store[0]);
     const unsigned bar_spec = (unsigned)__cvta_generic_to_shared(&bar_store[1]);
     const int np = rows >> log2n1;
-    auto row_of = [&](int ticket) { return ((ticket % np) << log2n1) + ticket / np; };   // k1-major, see k_row32
+    const int tickets = rows * nsn;
+    auto row_of = [&](int ticket) { const int r = ticket / nsn; return ((r % np) << log2n1) + r / np; };   // k1-major, see k_row32
     auto fetch = [&](const float2 *src, unsigned bar) {                 // one thread; the buffer must be idle
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, ROW_BYTES);
@@ -774,13 +778,13 @@ k_row32_stream(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *
     }
     __syncthreads();
     int ticket = blockIdx.x;
-    if (gtid == 0 && ticket < rows) fetch(A + ((size_t)row_of(ticket) << L2), bar_row);
+    if (gtid == 0 && ticket < tickets) fetch(A + ((size_t)row_of(ticket) << L2), bar_row);
     unsigned parity = 0;
-    while (ticket < rows) {
-        const int row = row_of(ticket);
+    while (ticket < tickets) {
+        const int row = row_of(ticket), sn = ticket % nsn;
         int claimed = 0;
         if (gtid == 0) claimed = (int)gridDim.x + atomicAdd(next_row, 1);
-        const float2 *Sr = spec + ((size_t)(row & ((1 << log2n1) - 1)) << L2);
+        const float2 *Sr = spec + (size_t)sn * spec_stride + ((size_t)(row & ((1 << log2n1) - 1)) << L2);
         float2 v[32];
         AM_TL_SET(row);
         AM_TL(0);
@@ -826,9 +830,9 @@ k_row32_stream(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *
         __syncthreads();
         AM_TL(5);
         const int next = s_next;
-        I::run_hook(v, sm, gtid, tw, [&] { if (gtid == 0 && next < rows) fetch(A + ((size_t)row_of(next) << L2), bar_row); });
+        I::run_hook(v, sm, gtid, tw, [&] { if (gtid == 0 && next < tickets) fetch(A + ((size_t)row_of(next) << L2), bar_row); });
         AM_TL(6);
-        float2 *Or = (MODE == ROW_INVERSE ? Bout : A) + ((size_t)row << L2);
+        float2 *Or = (MODE == ROW_INVERSE ? Bout + (size_t)sn * b_stride : A) + ((size_t)row << L2);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             int idx, t;

@@ -12,7 +12,11 @@
 //   k_chunk_peaks   one CTA per chunk: chunk minimum -> exact-safe candidate filter
 //                   (prominence <= height - chunk_min) -> warp-cooperative prominence
 //                   walks that skip whole tiles through the min/max summaries ->
-//                   min-distance suppression (block argmax loop) -> append to the output
+//                   min-distance suppression (block argmax loop) -> append to the output.
+//                   Candidates are taken in descending bands of height: a band holds at most
+//                   max_peaks_per_chunk candidates, and the descent stops as soon as the kept peaks
+//                   cover the chunk under the minimum distance (nothing lower can survive), so loud
+//                   or tonal material with millions of local maxima per chunk costs a few bands.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -95,6 +99,20 @@ k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin
 }
 
 
+struct PeakOut {
+    DevPeak *peaks;                 // global output list
+    unsigned long long cap;
+    unsigned long long *count;      // appended entries (may exceed cap: overflow is detected by the host)
+    unsigned *flags;                // FLAG_OVERFLOW | FLAG_NEED_DENSE (some chunk is marked in redo[])
+    // summary mode: redo[snippet * redo_stride + chunk - redo_first] = 1 marks a chunk whose peaks the run records
+    // cannot give exactly; it emits nothing and the host repeats exactly those chunks on a dense correlation
+    unsigned char *redo;
+    long long redo_first, redo_stride;
+};
+__device__ __forceinline__ long long redo_index(const PeakOut &o, unsigned snippet, long long chunk) {
+    return (long long)snippet * o.redo_stride + (chunk - o.redo_first);
+}
+
 // ---- summary mode -------------------------------------------------------------------------
 // k_col_inv's summary epilogue leaves, for every aligned run of 16 outputs, a record {min, max, first, last}
 // and the 16 values themselves only where max >= theta.  A chunk's outputs start run-aligned (C % 16 == 0);
@@ -103,34 +121,34 @@ k_tile_minmax(const float *__restrict__ c, ChunkGeom g, float *__restrict__ tmin
 // Any other geometry sets FLAG_NEED_DENSE and the host repeats the call with the dense correlation.
 constexpr unsigned FLAG_OVERFLOW = 1u, FLAG_NEED_DENSE = 2u;
 
-// The records live in two arrays so that the tile pass (which only needs min / max) reads 8 bytes per run:
-//   mm[r] = {min, max},  fl[r] = {first, last}   of the run of outputs [16 r, 16 r + 16) of the segment buffer
+// One 16-byte record per run: rec[r] = {min, max, first, last} of the outputs [16 r, 16 r + 16) of the segment
+// buffer.  (Measured on B200: splitting it into {min, max} / {first, last} arrays so that the tile pass reads 8
+// bytes per run costs the inverse column kernel two scattered 8-byte stores per run instead of one 16-byte store:
+// k_col_inv 5.7 -> 6.8 ms per 24 h, tile pass 0.70 -> 0.82 ms.  One array it is.)
 struct RunRecs {
-    float2 *mm, *fl;
-    __host__ __device__ RunRecs offset(long long runs) const { return RunRecs{mm + runs, fl + runs}; }
+    float4 *rec;
+    __host__ __device__ RunRecs offset(long long runs) const { return RunRecs{rec + runs}; }
 };
 
 struct RunView {
-    const float2 *mm, *fl;  // records of this chunk, [0] = run of the chunk's first output
+    const float4 *rec;      // records of this chunk, [0] = run of the chunk's first output
     long long nr_full;      // full runs
     int pv;                 // valid outputs of run nr_full (0: there is no partial run)
     bool masked;            // the partial run's record covers only the valid outputs
     __device__ __forceinline__ long long total() const { return nr_full + (pv ? 1 : 0); }
     __device__ __forceinline__ int count(long long r) const { return r == nr_full ? pv : 16; }
     __device__ __forceinline__ void minmax(long long r, float &mn, float &mx) const {
-        if (r == nr_full && !masked) { mn = mx = __ldg(fl + r).x; return; }
-        const float2 q = __ldg(mm + r);
-        mn = q.x; mx = q.y;
+        const float4 q = __ldg(rec + r);
+        if (r == nr_full && !masked) { mn = q.z; mx = q.z; } else { mn = q.x; mx = q.y; }
     }
-    __device__ __forceinline__ float first(long long r) const { return __ldg(fl + r).x; }
-    __device__ __forceinline__ float last(long long r) const { return __ldg(fl + r).y; }
+    __device__ __forceinline__ float first(long long r) const { return __ldg(rec + r).z; }
+    __device__ __forceinline__ float last(long long r) const { return __ldg(rec + r).w; }
 };
 __device__ __forceinline__ RunView make_run_view(const RunRecs &rsum, const ChunkGeom &g, long long chunk, long long V,
                                                  unsigned snippet) {
     RunView rv;
     const long long cs = g.C * chunk - g.c_g0;
-    rv.mm = rsum.mm + ((snippet * g.c_stride + cs) >> 4);
-    rv.fl = rsum.fl + ((snippet * g.c_stride + cs) >> 4);
+    rv.rec = rsum.rec + ((snippet * g.c_stride + cs) >> 4);
     rv.nr_full = V >> 4;
     rv.pv = (int)(V & 15);
     rv.masked = (cs + V == g.seg_end);
@@ -140,14 +158,17 @@ __device__ __forceinline__ RunView make_run_view(const RunRecs &rsum, const Chun
 // grid (ceil(tiles_stride / 8), chunks in segment, snippets), 256 threads: one tile (64 runs) per warp
 __global__ void __launch_bounds__(256)
 k_tile_from_runs(RunRecs rsum, ChunkGeom g, float *__restrict__ tmin, float *__restrict__ tmax,
-                 unsigned *flags) {
+                 PeakOut out) {
     const long long chunk = g.first_chunk + blockIdx.y;
     const long long V = chunk_valid_len(g, chunk);
     const int lane = threadIdx.x & 31;
     const long long tile = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if ((tile << TP_LOG2) >= V) return;
     const RunView rv = make_run_view(rsum, g, chunk, V, blockIdx.z);
-    if (rv.pv > 1 && !rv.masked && lane == 0) atomicOr(flags, FLAG_NEED_DENSE);
+    if (rv.pv > 1 && !rv.masked && lane == 0 && tile == 0) {     // a partial last run the records cannot represent
+        out.redo[redo_index(out, blockIdx.z, chunk)] = 1;
+        atomicOr(out.flags, FLAG_NEED_DENSE);
+    }
     float mn = CUDART_INF_F, mx = -CUDART_INF_F;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -345,21 +366,20 @@ __device__ float walk_min(const float *__restrict__ y, long long V, const float 
     return m;
 }
 
-struct PeakOut {
-    DevPeak *peaks;                 // global output list
-    unsigned long long cap;
-    unsigned long long *count;      // appended entries (may exceed cap: overflow is detected by the host)
-    unsigned *flags;                // bit 0: per-chunk candidate list overflow
-};
-
 // dynamic shared memory: [2 * sm_tiles floats: the chunk's tile summaries, when they fit] +
-// pk_cap * (2*u32 + 4*f32 + u8).   grid = (chunks in segment, snippets), 256 threads
+// pk_cap * (2*u32 + 4*f32 + u8) candidates of the current band + pk_cap * (2*u32 + 4*f32) kept peaks.
+// grid = (chunks in segment, snippets), 256 threads
 // SUM: summary mode -- `rsum` holds the run records, only runs with max >= theta are present in c.
+// only_flagged: dense repeat -- work only on the chunks marked in out.redo[].
+constexpr int MAX_BANDS = 64;
+__host__ __device__ inline size_t chunk_peaks_smem(int pk_cap, int sm_tiles) {
+    return (size_t)sm_tiles * 8 + (size_t)pk_cap * (2 * 4 + 4 * 4) * 2 + (size_t)pk_cap + 16;
+}
 template <bool SUM>
 __global__ void __launch_bounds__(256)
 k_chunk_peaks(const float *__restrict__ c, RunRecs rsum, float theta, ChunkGeom g,
               const float *__restrict__ tmin_all, const float *__restrict__ tmax_all, float min_prom,
-              unsigned long long min_dist, int pk_cap, int sm_tiles, PeakOut out) {
+              unsigned long long min_dist, int pk_cap, int sm_tiles, PeakOut out, int only_flagged) {
     extern __shared__ unsigned char smraw[];
     float *s_tmin = (float *)smraw, *s_tmax = s_tmin + sm_tiles;
     unsigned *p_start = (unsigned *)(s_tmax + sm_tiles);
@@ -368,17 +388,26 @@ k_chunk_peaks(const float *__restrict__ c, RunRecs rsum, float theta, ChunkGeom 
     float *p_prom = p_h + pk_cap;
     float *p_ld = p_prom + pk_cap;
     float *p_rd = p_ld + pk_cap;
-    unsigned char *p_alive = (unsigned char *)(p_rd + pk_cap);
-    __shared__ float s_red[8];
+    unsigned *k_start = (unsigned *)(p_rd + pk_cap);                // kept peaks (emitted at the end)
+    unsigned *k_end = k_start + pk_cap;
+    float *k_h = (float *)(k_end + pk_cap);
+    float *k_prom = k_h + pk_cap;
+    float *k_ld = k_prom + pk_cap;
+    float *k_rd = k_ld + pk_cap;
+    unsigned char *p_alive = (unsigned char *)(k_rd + pk_cap);
+    __shared__ float s_red[8], s_red2[8];
     __shared__ int s_redi[8];
-    __shared__ int s_ncand, s_win;
-    __shared__ float s_cmin;
+    __shared__ int s_ncand, s_win, s_nkept;
+    __shared__ unsigned long long s_base;
+    __shared__ float s_cmin, s_gmax;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long chunk = g.first_chunk + blockIdx.x;
     const long long V = chunk_valid_len(g, chunk);
     if (V < 3) return;                                              // endpoints are never peaks
     const unsigned snippet_id = blockIdx.y;
+    const long long ridx = out.redo ? redo_index(out, snippet_id, chunk) : 0;
+    if (only_flagged ? !out.redo[ridx] : (SUM && out.redo[ridx])) return;   // dense repeat: marked chunks only; summary: skip chunks k_tile_from_runs rejected
     const float *y = c + snippet_id * g.c_stride + (g.C * chunk - g.c_g0);
     const float *tmin = tmin_all + ((size_t)snippet_id * gridDim.x + blockIdx.x) * g.tiles_stride;
     const float *tmax = tmax_all + ((size_t)snippet_id * gridDim.x + blockIdx.x) * g.tiles_stride;
@@ -390,179 +419,292 @@ k_chunk_peaks(const float *__restrict__ c, RunRecs rsum, float theta, ChunkGeom 
         tmax = s_tmax;
     }
 
-    // (a) chunk minimum
-    float mn = CUDART_INF_F;
-    for (long long t = tid; t < ntiles; t += 256) mn = fminf(mn, tmin[t]);
+    // (a) chunk minimum and maximum
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    for (long long t = tid; t < ntiles; t += 256) { mn = fminf(mn, tmin[t]); mx = fmaxf(mx, tmax[t]); }
     mn = warp_min(mn);
-    if (lane == 0) s_red[warp] = mn;
-    if (tid == 0) s_ncand = 0;
+    mx = warp_max(mx);
+    if (lane == 0) { s_red[warp] = mn; s_red2[warp] = mx; }
+    if (tid == 0) { s_ncand = 0; s_nkept = 0; }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < 8; ++w) mn = fminf(mn, s_red[w]);
+        for (int w = 1; w < 8; ++w) { mn = fminf(mn, s_red[w]); mx = fmaxf(mx, s_red2[w]); }
         s_cmin = mn;
+        s_gmax = mx;
     }
     __syncthreads();
-    const float cmin = s_cmin;
+    const float cmin = s_cmin, gmax = s_gmax;
+    if (!(gmax - cmin >= min_prom)) return;                         // no sample can reach the prominence: no peaks
+    auto mark_dense = [&]() {                                       // this chunk is repeated on a dense correlation; emits nothing here
+        if (tid == 0) { out.redo[ridx] = 1; atomicOr(out.flags, FLAG_NEED_DENSE); }
+    };
     RunView rv;
+    // Summary mode is exact while every run that can hold a candidate (max - cmin >= min_prom) or stop a walk
+    // (max > h) is stored, i.e. theta <= min_prom + cmin.  Otherwise (stream much louder than the snippet, tonal
+    // material) only candidates of height >= theta can be examined: the result is still exact if the peaks kept
+    // among those cover the whole chunk under the minimum distance -- anything lower is then suppressed whatever
+    // its prominence.  If they do not, the chunk is marked for the dense repeat.
+    bool may_abort = false;
     if constexpr (SUM) {
         rv = make_run_view(rsum, g, chunk, V, snippet_id);
-        // every run that can hold a candidate (max - cmin >= min_prom) or stop a walk (max > h) must be stored:
-        // guaranteed when theta <= min_prom + cmin, otherwise the host redoes the call densely
         if (!(min_prom + cmin >= theta)) {
-            if (tid == 0) atomicOr(out.flags, FLAG_NEED_DENSE);
-            return;
+            may_abort = true;
+            if (min_dist == 0 || gmax < theta) { mark_dense(); return; }
         }
     }
+    const float lo_floor = may_abort ? theta : -CUDART_INF_F;       // lowest height the descent has to reach
+    const float b0 = may_abort ? theta : cmin;                      // finite stand-in for the bisection
 
-    // (b) candidates: local maxima whose upper bound h - chunk_min on the prominence passes.
-    // prominence = h - max(lmin, rmin) <= h - chunk_min (fp subtraction is monotone), so no
-    // peak that find_peaks would keep is dropped here.
-    for (long long t = warp; t < ntiles; t += 8) {
-        if (!(tmax[t] - cmin >= min_prom)) continue;                // warp-uniform
-        long long k0 = t << TP_LOG2;
-        if constexpr (SUM) {
-            // qualifying runs of the tile (two per lane); a lane scans its run serially -- such runs are rare
-            auto val = [&](long long a) { return (a & 15) == 0 ? rv.first(a >> 4) : __ldg(y + a); };
-            for (int i = 0; i < 2; ++i) {
-                const long long r = (t << 6) + i * 32 + lane;
-                if (r >= rv.total()) continue;
-                float rmn, rmx;
-                rv.minmax(r, rmn, rmx);
-                if (!(rmx - cmin >= min_prom)) continue;
-                const int cnt = rv.count(r);
-                for (int sidx = 0; sidx < cnt; ++sidx) {
-                    const long long k = (r << 4) + sidx;
-                    if (k < 1 || k >= V - 1) continue;
-                    const float yk = __ldg(y + k);
-                    const float prev = sidx ? __ldg(y + k - 1) : rv.last(r - 1);
-                    if (!(prev < yk) || !(yk - cmin >= min_prom)) continue;
-                    long long a = k + 1;
-                    while (a < V - 1 && val(a) == yk) ++a;          // plateau (its runs have max >= yk >= theta)
-                    if (val(a) < yk) {
-                        int slot = atomicAdd(&s_ncand, 1);
-                        if (slot < pk_cap) {
-                            p_start[slot] = (unsigned)k;
-                            p_end[slot] = (unsigned)a;
-                            p_h[slot] = yk;
-                        }
-                    }
-                }
-            }
-            continue;
-        }
-        for (int it = 0; it < TP / 32; ++it) {
-            long long k = k0 + it * 32 + lane;
-            if (k >= 1 && k < V - 1) {
-                float yk = __ldg(y + k);
-                if (__ldg(y + k - 1) < yk && yk - cmin >= min_prom) {
-                    long long a = k + 1;
-                    while (a < V - 1 && __ldg(y + a) == yk) ++a;    // plateau
-                    if (__ldg(y + a) < yk) {
-                        int slot = atomicAdd(&s_ncand, 1);
-                        if (slot < pk_cap) {
-                            p_start[slot] = (unsigned)k;
-                            p_end[slot] = (unsigned)a;
-                            p_h[slot] = yk;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    int ncand = s_ncand;
-    if (ncand > pk_cap) {
-        if (tid == 0) atomicOr(out.flags, FLAG_OVERFLOW);
-        ncand = pk_cap;
-    }
-
-    // (c) exact prominence, one warp per candidate
-    for (int i = warp; i < ncand; i += 8) {
-        const float h = p_h[i];
-        const long long s = p_start[i], e = p_end[i];
-        float lmin, rmin;
-        if constexpr (SUM) {
-            lmin = walk_min_sum<-1>(y, rv, V, tmin, tmax, s, h);
-            rmin = walk_min_sum<+1>(y, rv, V, tmin, tmax, e, h);
-        } else {
-            lmin = walk_min<-1>(y, V, tmin, tmax, s, h);
-            rmin = walk_min<+1>(y, V, tmin, tmax, e, h);
-        }
-        if (lane == 0) {
-            float prom = h - fmaxf(lmin, rmin);
-            p_prom[i] = prom;
+    // (b) candidates of the band [lo, hi): local maxima whose upper bound h - chunk_min on the prominence passes.
+    // prominence = h - max(lmin, rmin) <= h - chunk_min (fp subtraction is monotone), so no peak that find_peaks
+    // would keep is dropped here.  Stops early once the list has overflowed (the caller then narrows the band).
+    auto enumerate = [&](float lo, float hi) {
+        for (long long t = warp; t < ntiles; t += 8) {
+            if (*(volatile int *)&s_ncand > pk_cap) break;
+            const float tm = tmax[t];
+            if (!(tm - cmin >= min_prom) || !(tm >= lo)) continue;  // warp-uniform
+            const long long k0 = t << TP_LOG2;
             if constexpr (SUM) {
-                p_ld[i] = h - ((s & 15) ? __ldg(y + s - 1) : rv.last((s >> 4) - 1));
-                p_rd[i] = h - ((e & 15) ? __ldg(y + e) : rv.first(e >> 4));
-            } else {
-                p_ld[i] = h - __ldg(y + s - 1);
-                p_rd[i] = h - __ldg(y + e);
+                // qualifying runs of the tile (two per lane); a lane scans its run serially
+                auto val = [&](long long a) { return (a & 15) == 0 ? rv.first(a >> 4) : __ldg(y + a); };
+                for (int i = 0; i < 2; ++i) {
+                    const long long r = (t << 6) + i * 32 + lane;
+                    if (r >= rv.total()) continue;
+                    float rmn, rmx;
+                    rv.minmax(r, rmn, rmx);
+                    if (!(rmx - cmin >= min_prom) || !(rmx >= lo)) continue;
+                    const int cnt = rv.count(r);
+                    for (int sidx = 0; sidx < cnt; ++sidx) {
+                        const long long k = (r << 4) + sidx;
+                        if (k < 1 || k >= V - 1) continue;
+                        const float yk = __ldg(y + k);
+                        if (!(yk >= lo) || !(yk < hi) || !(yk - cmin >= min_prom)) continue;
+                        const float prev = sidx ? __ldg(y + k - 1) : rv.last(r - 1);
+                        if (!(prev < yk)) continue;
+                        long long a = k + 1;
+                        while (a < V - 1 && val(a) == yk) ++a;      // plateau (its runs have max >= yk >= theta)
+                        if (val(a) < yk) {
+                            int slot = atomicAdd(&s_ncand, 1);
+                            if (slot < pk_cap) {
+                                p_start[slot] = (unsigned)k;
+                                p_end[slot] = (unsigned)a;
+                                p_h[slot] = yk;
+                            }
+                        }
+                    }
+                }
+                continue;
             }
-            p_alive[i] = prom >= min_prom;                          // with_min_prominence, :227
-        }
-    }
-    __syncthreads();
-
-    auto emit = [&](int i) {
-        unsigned long long slot = atomicAdd(out.count, 1ull);
-        if (slot < out.cap) {
-            DevPeak p;
-            const unsigned long long off = (unsigned long long)(g.C * chunk);   // offset_range, lib.rs:8-10
-            p.start = off + p_start[i];
-            p.end = off + p_end[i];
-            p.height = p_h[i];
-            p.prominence = p_prom[i];
-            p.left_diff = p_ld[i];
-            p.right_diff = p_rd[i];
-            p.snippet_id = snippet_id;
-            p.chunk = (unsigned)chunk;
-            out.peaks[slot] = p;
+            for (int it = 0; it < TP / 32; ++it) {
+                long long k = k0 + it * 32 + lane;
+                if (k >= 1 && k < V - 1) {
+                    float yk = __ldg(y + k);
+                    if (yk >= lo && yk < hi && __ldg(y + k - 1) < yk && yk - cmin >= min_prom) {
+                        long long a = k + 1;
+                        while (a < V - 1 && __ldg(y + a) == yk) ++a;    // plateau
+                        if (__ldg(y + a) < yk) {
+                            int slot = atomicAdd(&s_ncand, 1);
+                            if (slot < pk_cap) {
+                                p_start[slot] = (unsigned)k;
+                                p_end[slot] = (unsigned)a;
+                                p_h[slot] = yk;
+                            }
+                        }
+                    }
+                }
+            }
         }
     };
+    auto mid_of = [](unsigned a, unsigned b) { return ((unsigned long long)a + b) / 2; };
+    // do the kept peaks leave no position of [1, V-2] at distance >= min_dist from all of them?
+    auto covered = [&]() -> bool {
+        const int nk = s_nkept;
+        bool ok = true;
+        for (int i = tid; i < nk; i += 256) {
+            const unsigned long long mi = mid_of(k_start[i], k_end[i]);
+            unsigned long long next = ~0ull;
+            bool has_prev = false;
+            for (int j = 0; j < nk; ++j) {
+                const unsigned long long mj = mid_of(k_start[j], k_end[j]);
+                if (mj > mi && mj < next) next = mj;
+                if (mj < mi) has_prev = true;
+            }
+            if (!has_prev && mi - 1 >= min_dist && mi >= 1 + min_dist) ok = false;            // position 1 is out of reach
+            if (next == ~0ull) { if ((unsigned long long)(V - 2) >= mi + min_dist) ok = false; }
+            else if (next - mi >= 2 * min_dist) ok = false;
+        }
+        return __syncthreads_and(ok) && nk > 0;
+    };
 
-    // (d) with_min_distance (:228): greedy in descending height, ties by lower position
-    if (min_dist == 0) {
-        for (int i = tid; i < ncand; i += 256)
-            if (p_alive[i]) emit(i);
+    float hi = CUDART_INF_F, width = 0.f;
+    bool finished = false;
+    for (int band = 0; band < MAX_BANDS && !finished; ++band) {
+        // choose the band's lower edge: the floor if the candidates fit, else bisect towards the band's top
+        const float top = (hi < CUDART_INF_F) ? hi : gmax;
+        float lo = lo_floor;
+        if (band > 0 && width > 0.f && hi - 2.f * width > b0) lo = hi - 2.f * width;
+        int ncand = 0;
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) s_ncand = 0;
+            __syncthreads();
+            enumerate(lo, hi);
+            __syncthreads();
+            ncand = s_ncand;
+            if (ncand <= pk_cap) break;
+            const float from = (lo > -CUDART_INF_F) ? lo : b0;
+            const float nlo = from + 0.5f * (top - from);
+            if (!(nlo > from) || !(nlo <= top) || nlo == lo) {      // cannot narrow further: > pk_cap equal-height maxima
+                if (tid == 0) atomicOr(out.flags, FLAG_OVERFLOW);
+                return;
+            }
+            lo = nlo;
+        }
+        const bool reached_floor = !(lo > lo_floor);
+
+        // (c) exact prominence, one warp per candidate
+        for (int i = warp; i < ncand; i += 8) {
+            const float h = p_h[i];
+            const long long s = p_start[i], e = p_end[i];
+            float lmin, rmin;
+            if constexpr (SUM) {
+                lmin = walk_min_sum<-1>(y, rv, V, tmin, tmax, s, h);
+                rmin = walk_min_sum<+1>(y, rv, V, tmin, tmax, e, h);
+            } else {
+                lmin = walk_min<-1>(y, V, tmin, tmax, s, h);
+                rmin = walk_min<+1>(y, V, tmin, tmax, e, h);
+            }
+            if (lane == 0) {
+                float prom = h - fmaxf(lmin, rmin);
+                p_prom[i] = prom;
+                if constexpr (SUM) {
+                    p_ld[i] = h - ((s & 15) ? __ldg(y + s - 1) : rv.last((s >> 4) - 1));
+                    p_rd[i] = h - ((e & 15) ? __ldg(y + e) : rv.first(e >> 4));
+                } else {
+                    p_ld[i] = h - __ldg(y + s - 1);
+                    p_rd[i] = h - __ldg(y + e);
+                }
+                p_alive[i] = prom >= min_prom;                      // with_min_prominence, :227
+            }
+        }
+        __syncthreads();
+
+        auto keep = [&](int i) {                                    // one thread; returns false when the kept list is full
+            const int k = s_nkept;
+            if (k >= pk_cap) return false;
+            k_start[k] = p_start[i]; k_end[k] = p_end[i]; k_h[k] = p_h[i];
+            k_prom[k] = p_prom[i]; k_ld[k] = p_ld[i]; k_rd[k] = p_rd[i];
+            s_nkept = k + 1;
+            return true;
+        };
+        // (d) with_min_distance (:228): greedy in descending height, ties by lower position.  Peaks kept in
+        // earlier (higher) bands come first in that order, so they suppress this band's candidates up front.
+        if (min_dist == 0) {
+            // no suppression: every alive candidate is a result.  (may_abort chunks never get here.)  Flush the
+            // kept list to the output whenever it fills up.
+            for (int i0 = 0; i0 < ncand; i0 += 256) {
+                const int i = i0 + tid;
+                const bool a = i < ncand && p_alive[i];
+                const unsigned long long slot = a ? atomicAdd(out.count, 1ull) : 0;
+                if (a && slot < out.cap) {
+                    DevPeak p;
+                    const unsigned long long off = (unsigned long long)(g.C * chunk);
+                    p.start = off + p_start[i]; p.end = off + p_end[i]; p.height = p_h[i]; p.prominence = p_prom[i];
+                    p.left_diff = p_ld[i]; p.right_diff = p_rd[i]; p.snippet_id = snippet_id; p.chunk = (unsigned)chunk;
+                    out.peaks[slot] = p;
+                }
+            }
+        } else {
+            const int nk0 = s_nkept;
+            for (int i = tid; i < ncand; i += 256) {
+                if (!p_alive[i]) continue;
+                const unsigned long long mi = mid_of(p_start[i], p_end[i]);
+                for (int k = 0; k < nk0; ++k) {
+                    const unsigned long long mk = mid_of(k_start[k], k_end[k]);
+                    if ((mi > mk ? mi - mk : mk - mi) < min_dist) { p_alive[i] = 0; break; }
+                }
+            }
+            __syncthreads();
+            for (;;) {
+                float bh = -CUDART_INF_F;
+                int bi = -1;
+                for (int i = tid; i < ncand; i += 256) {
+                    if (p_alive[i]) {
+                        float h = p_h[i];
+                        if (bi < 0 || h > bh || (h == bh && p_start[i] < p_start[bi])) { bh = h; bi = i; }
+                    }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    float oh = __shfl_xor_sync(0xffffffffu, bh, o);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (oi >= 0 && (bi < 0 || oh > bh || (oh == bh && p_start[oi] < p_start[bi]))) { bh = oh; bi = oi; }
+                }
+                if (lane == 0) { s_red[warp] = bh; s_redi[warp] = bi; }
+                __syncthreads();
+                if (tid == 0) {
+                    for (int w = 1; w < 8; ++w) {
+                        float oh = s_red[w];
+                        int oi = s_redi[w];
+                        if (oi >= 0 && (bi < 0 || oh > bh || (oh == bh && p_start[oi] < p_start[bi]))) { bh = oh; bi = oi; }
+                    }
+                    if (bi >= 0 && !keep(bi)) bi = -2;              // kept list full
+                    s_win = bi;
+                }
+                __syncthreads();
+                const int win = s_win;
+                if (win == -2) {
+                    if (tid == 0) atomicOr(out.flags, FLAG_OVERFLOW);
+                    return;
+                }
+                if (win < 0) break;
+                const unsigned long long mw = mid_of(p_start[win], p_end[win]);
+                for (int i = tid; i < ncand; i += 256) {
+                    if (p_alive[i]) {
+                        unsigned long long mi = mid_of(p_start[i], p_end[i]);
+                        unsigned long long d = mi > mw ? mi - mw : mw - mi;
+                        if (i == win || d < min_dist) p_alive[i] = 0;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        // done when the descent has reached its floor, or when nothing lower can survive the minimum distance
+        if (reached_floor) {
+            if (may_abort && !covered()) { mark_dense(); return; }  // peaks below theta may exist: not decidable from the records
+            finished = true;
+        } else if (min_dist > 0 && covered()) {
+            finished = true;
+        } else {
+            width = top - lo;
+            hi = lo;
+        }
+    }
+    if (!finished) {                                                // too many bands: the kept peaks never covered the chunk
+        if (tid == 0) atomicOr(out.flags, FLAG_OVERFLOW);
         return;
     }
-    for (;;) {
-        float bh = -CUDART_INF_F;
-        int bi = -1;
-        for (int i = tid; i < ncand; i += 256) {
-            if (p_alive[i]) {
-                float h = p_h[i];
-                if (bi < 0 || h > bh || (h == bh && p_start[i] < p_start[bi])) { bh = h; bi = i; }
-            }
+
+    // emit the kept peaks: one reservation per chunk
+    const int nk = s_nkept;
+    if (nk == 0) return;
+    if (tid == 0) s_base = atomicAdd(out.count, (unsigned long long)nk);
+    __syncthreads();
+    const unsigned long long base = s_base;
+    const unsigned long long off = (unsigned long long)(g.C * chunk);   // offset_range, lib.rs:8-10
+    for (int i = tid; i < nk; i += 256) {
+        if (base + i < out.cap) {
+            DevPeak p;
+            p.start = off + k_start[i];
+            p.end = off + k_end[i];
+            p.height = k_h[i];
+            p.prominence = k_prom[i];
+            p.left_diff = k_ld[i];
+            p.right_diff = k_rd[i];
+            p.snippet_id = snippet_id;
+            p.chunk = (unsigned)chunk;
+            out.peaks[base + i] = p;
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            float oh = __shfl_xor_sync(0xffffffffu, bh, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (oi >= 0 && (bi < 0 || oh > bh || (oh == bh && p_start[oi] < p_start[bi]))) { bh = oh; bi = oi; }
-        }
-        if (lane == 0) { s_red[warp] = bh; s_redi[warp] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < 8; ++w) {
-                float oh = s_red[w];
-                int oi = s_redi[w];
-                if (oi >= 0 && (bi < 0 || oh > bh || (oh == bh && p_start[oi] < p_start[bi]))) { bh = oh; bi = oi; }
-            }
-            s_win = bi;
-            if (bi >= 0) emit(bi);
-        }
-        __syncthreads();
-        const int win = s_win;
-        if (win < 0) break;
-        const unsigned long long mw = ((unsigned long long)p_start[win] + p_end[win]) / 2;
-        for (int i = tid; i < ncand; i += 256) {
-            if (p_alive[i]) {
-                unsigned long long mi = ((unsigned long long)p_start[i] + p_end[i]) / 2;
-                unsigned long long d = mi > mw ? mi - mw : mw - mi;
-                if (i == win || d < min_dist) p_alive[i] = 0;
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -577,8 +719,7 @@ __global__ void k_debug_make_runs(float *__restrict__ c, long long n, float thet
     float *p = c + (r << 4);
     float mn = p[0], mx = p[0], last = p[0];
     for (int i = 1; i < valid; ++i) { mn = fminf(mn, p[i]); mx = fmaxf(mx, p[i]); last = p[i]; }
-    rsum.mm[r] = make_float2(mn, mx);
-    rsum.fl[r] = make_float2(p[0], last);
+    rsum.rec[r] = make_float4(mn, mx, p[0], last);
     if (!(mx >= theta))
         for (int i = 0; i < valid; ++i) p[i] = __int_as_float(0x7fc00000);
 }

@@ -267,6 +267,65 @@ class CudaConvolve:
         return buf, got.value
 
 
+class StreamSession:
+    """Push session (am_stream_begin / push / finish): calc_chunks for a decoder that yields the stream in pieces, the
+    shape of the reference's lazy sample iterator (mp3_reader.rs:13-66, matcher/mod.rs:71-83).
+
+        with StreamSession(algo, max_frames=claimed_samples) as st:
+            for block in decoder:            # numpy int16 (mono or [frames, 2]) or float32 blocks of any size
+                st.push(block)
+        peaks = st.peaks
+    """
+
+    def __init__(self, algo: CudaConvolve, max_frames: int, fmt: int = N.FMT_I16_MONO, scale: bool = True, cap: int = 1 << 16):
+        self._algo, self._cap, self.peaks, self._fmt = algo, cap, None, fmt
+        s = C.c_void_p()
+        N.check(N.lib().am_stream_begin(algo._h, int(max_frames), fmt, int(bool(scale)), C.byref(s)))
+        self._s = s
+
+    def push(self, block) -> None:
+        ptr, frames, fmt, mem, keep = _describe(block)
+        if mem != N.MEM_HOST or fmt != self._fmt:
+            raise TypeError("push() takes host blocks in the session's sample format")
+        N.check(N.lib().am_stream_push(self._s, ptr, frames))
+
+    def finish(self) -> list[Peak]:
+        buf = (N.AmPeak * self._cap)()
+        got = C.c_size_t()
+        s, self._s = self._s, None
+        N.check(N.lib().am_stream_finish(s, buf, self._cap, C.byref(got)))
+        self.peaks = [Peak._from_native(buf[i]) for i in range(got.value)]
+        return self.peaks
+
+    def abort(self) -> None:
+        if self._s:
+            N.lib().am_stream_abort(self._s)
+            self._s = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None and self._s:
+            self.finish()
+        else:
+            self.abort()
+        return False
+
+
+def calc_chunks_streamed(sr: int, blocks, max_frames: int, algo_with_sample: CudaConvolve, scale: bool, config: Config,
+                         fmt: int = N.FMT_I16_MONO, cap: int = 1 << 16) -> list[Peak]:
+    """calc_chunks (audio_matcher.rs:88-141) over an iterable of decoded blocks with a claimed length (`with_size`,
+    mod.rs:83): matching overlaps the producer."""
+    if int(sr) != algo_with_sample.sr:
+        raise ValueError(f"sample rate mismatch {algo_with_sample.sr} != {sr}")
+    algo_with_sample.set_config(config)
+    with StreamSession(algo_with_sample, max_frames, fmt, scale, cap) as st:
+        for b in blocks:
+            st.push(b)
+    return st.peaks
+
+
 def calc_chunks(sr: int, m_samples, algo_with_sample: CudaConvolve, scale: bool, config: Config,
                 cap: int = 1 << 16) -> list[Peak]:
     """calc_chunks (audio_matcher.rs:88-141).  `m_samples` is the decoded stream (numpy array in host

@@ -32,10 +32,10 @@ int main(int argc, char **argv) {
     cudaFuncSetAttribute(k_row32_stream<L2, ROW_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     const int rows = pairs << L1, ctas = argc > 1 ? atoi(argv[1]) : 296;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int it = 0; it < 2; ++it) { cudaMemset(ctr, 0, 4); k_row32_stream<L2, ROW_FUSED><<<ctas, Cfg::THREADS, Cfg::SMEM>>>(A, S, nullptr, L1, rows, dtw, ctr); }
+    for (int it = 0; it < 2; ++it) { cudaMemset(ctr, 0, 4); k_row32_stream<L2, ROW_FUSED><<<ctas, Cfg::THREADS, Cfg::SMEM>>>(A, S, nullptr, L1, rows, dtw, ctr, 1, 0, 0); }
     cudaMemset(ctr, 0, 4);
     cudaEventRecord(e0);
-    k_row32_stream<L2, ROW_FUSED><<<ctas, Cfg::THREADS, Cfg::SMEM>>>(A, S, nullptr, L1, rows, dtw, ctr);
+    k_row32_stream<L2, ROW_FUSED><<<ctas, Cfg::THREADS, Cfg::SMEM>>>(A, S, nullptr, L1, rows, dtw, ctr, 1, 0, 0);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("k_row32_stream %.1f us for %d rows (%s)\n", ms * 1e3, rows, cudaGetErrorString(cudaGetLastError()));
@@ -60,10 +60,10 @@ int main(int argc, char **argv) {
     cudaFuncSetAttribute(k_row32_stream<L2, ROW_INVERSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     
     
-    for (int it = 0; it < 2; ++it) { cudaMemset(ctr, 0, 4); k_row32_stream<L2, ROW_INVERSE><<<ctas, Cfg::THREADS, Cfg::SMEM>>>(A, S, Bbuf, L1, rows, dtw, ctr); }
+    for (int it = 0; it < 2; ++it) { cudaMemset(ctr, 0, 4); k_row32_stream<L2, ROW_INVERSE><<<ctas, Cfg::THREADS, Cfg::SMEM>>>(A, S, Bbuf, L1, rows, dtw, ctr, 1, 0, 0); }
     cudaMemset(ctr, 0, 4);
     cudaEventRecord(e0);
-    k_row32_stream<L2, ROW_INVERSE><<<ctas, Cfg::THREADS, Cfg::SMEM>>>(A, S, Bbuf, L1, rows, dtw, ctr);
+    k_row32_stream<L2, ROW_INVERSE><<<ctas, Cfg::THREADS, Cfg::SMEM>>>(A, S, Bbuf, L1, rows, dtw, ctr, 1, 0, 0);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
      cudaEventElapsedTime(&ms, e0, e1);
     printf("k_row32_stream<ROW_INVERSE> %.1f us for %d rows (%s)\n", ms * 1e3, rows, cudaGetErrorString(cudaGetLastError()));

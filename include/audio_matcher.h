@@ -194,6 +194,22 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
 am_status am_merge_peaks(am_peak *peaks, size_t n, uint32_t sr, double distance_s, am_peak *out, size_t cap,
                          size_t *n_out);
 
+/* ---- push session: calc_chunks for a stream that arrives piece by piece --------------------------------------
+ * The reference hands calc_chunks a lazy iterator of decoded frames with a claimed length (mp3_reader.rs:13-66,
+ * matcher/mod.rs:71-83).  A decoder thread calls am_stream_push with whatever it has decoded (host memory of any
+ * kind, any piece size; the buffer may be reused as soon as the call returns); the library collects the frames in a
+ * pinned ring, uploads them with one asynchronous copy per 32 MB and launches the transforms + peak search of a
+ * segment of logical chunks as soon as its frames are complete, so matching and upload overlap decoding.
+ * max_frames: upper bound of the stream length (the claimed length, mod.rs:78); the stream's true length is what has
+ * been pushed when am_stream_finish is called.  Results equal am_calc_chunks on the concatenated frames.
+ * Between begin and finish/abort the matcher's other compute entry points fail with AM_ERR_INVALID. */
+typedef struct am_stream_session am_stream_session;
+am_status am_stream_begin(am_matcher *h, size_t max_frames, am_sample_fmt fmt, int scale, am_stream_session **out);
+am_status am_stream_push(am_stream_session *s, const void *pcm, size_t frames);
+/* runs the last (partial) segment, the global sort + neighbour filter, and closes the session (also on error) */
+am_status am_stream_finish(am_stream_session *s, am_peak *out, size_t cap, size_t *n_out);
+void am_stream_abort(am_stream_session *s);
+
 /* ---- multi-GPU: one process per GPU, chunk-range shards, one all-gather of peak candidates ----------------
  * am_comm_get_unique_id: rank 0 creates the 128-byte id and hands it to the other ranks by any means (file, MPI,
  * torch.distributed ...); am_comm_init is collective over the nranks processes and binds the communicator to the

@@ -165,9 +165,10 @@ def test_summary_mode_small_cases(am, orc, row_log2):
 
 
 def test_summary_mode_falls_back_to_dense(am, orc):
-    """Geometries / data the run records cannot represent exactly must be redone densely, not approximated:
-    (a) a chunk whose last run holds more than one valid output in the middle of a segment (ov = m + 4),
-    (b) a chunk minimum below theta - prominence (stream much louder than the snippet)."""
+    """Geometries / data the run records cannot represent exactly must be done densely, not approximated:
+    (a) full windows whose last run holds more than one valid output (ov = m + 4): no summary pass at all,
+    (b) a chunk minimum below theta - prominence (stream much louder than the snippet): only the chunks whose kept
+        peaks do not cover them are repeated densely (am_stats.dense_chunks)."""
     sr, m = 8000, 4000
     pcm = orc.synth_pcm16(41, 0, sr * 43)
     snip = orc.synth_pcm16(42, 0, m)
@@ -179,21 +180,71 @@ def test_summary_mode_falls_back_to_dense(am, orc):
     conf = am.Config(chunk_size=5.0, overlap_length=ov_s, peak_config=am.PeakConfig(2.0, 0.13), fft_log2=20)
     algo = am.CudaConvolve(snip, sr=sr, config=conf)
     got = am.calc_chunks(sr, pcm, algo, True, conf)
-    assert algo.stats()["summary_mode"] == 2
+    assert algo.stats()["summary_mode"] == 0
     _assert_peaks(got, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
     algo.close()
     quiet = (snip // 4).astype(np.int16)                                   # snippet 12 dB below the stream: noisy scores
     sq = orc.pcm16_to_f32(quiet)
-    ref = orc.calc_chunks(x, sq, sr, orc.make_config(2.5, m / sr, 2.0, 0.3), scale=True, precision=64)
-    conf = am.Config(chunk_size=2.5, peak_config=am.PeakConfig(2.0, 0.3), fft_log2=20, max_peaks_per_chunk=8000)
-    algo = am.CudaConvolve(quiet, sr=sr, config=conf)
-    got = am.calc_chunks(sr, pcm, algo, True, conf)
-    assert algo.stats()["summary_mode"] == 2
-    _assert_peaks(got, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
-    algo.close()
+    for dist, pkcap in ((2.0, 0), (2.0, 48), (0.5, 200), (0.0, 0)):        # small caps force the descent through many height bands
+        ref = orc.calc_chunks(x, sq, sr, orc.make_config(2.5, m / sr, dist, 0.3), scale=True, precision=64, cap=1 << 18)
+        conf = am.Config(chunk_size=2.5, peak_config=am.PeakConfig(dist, 0.3), fft_log2=20, max_peaks_per_chunk=pkcap)
+        algo = am.CudaConvolve(quiet, sr=sr, config=conf)
+        got = am.calc_chunks(sr, pcm, algo, True, conf, cap=1 << 18)
+        st = algo.stats()
+        assert st["summary_mode"] in (1, 2) and (st["summary_mode"] == 2) == (st["dense_chunks"] > 0), st
+        assert st["dense_chunks"] <= st["chunks"]
+        assert len(ref) > 3
+        _assert_peaks(got, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+        algo.close()
 
 
-@pytest.mark.parametrize("seed,dist,prom,maxpk", [(1, 0.0, 0.09, 8000), (2, 1.0, 0.09, 8000), (3, 3.0, 0.11, 0), (4, 480.0, 0.13, 0)])
+def _coloured_noise(rng, n, rho, rms):
+    """AR(1) noise x[i] = rho x[i-1] + e[i], scaled to `rms` (int16 PCM)."""
+    from scipy import signal
+    e = rng.standard_normal(n)
+    x = signal.lfilter([1.0], [1.0, -rho], e)
+    x *= rms / np.sqrt(np.mean(x * x))
+    return np.clip(np.round(x), -32768, 32767).astype(np.int16)
+
+
+@pytest.mark.parametrize("kind", ["loud_white", "coloured", "tonal"])
+def test_loud_and_coloured_streams_vs_oracle(am, orc, kind):
+    """Programme material is rarely white noise at the snippet's level: scores are normalised by the snippet's energy
+    only (audio_matcher.rs:321-329), so a stream 12 dB louder, an AR(1) (coloured) spectrum or a tonal stream push the
+    chunk minimum far below theta - prominence and fill every chunk with local maxima.  Results must still equal the
+    oracle's, through summary mode (block 2^20) and through the dense path (block 2^15), without raising
+    max_peaks_per_chunk."""
+    rng = np.random.default_rng({"loud_white": 11, "coloured": 12, "tonal": 13}[kind])
+    sr, m, n = 8000, 4000, 8000 * 42 + 123
+    if kind == "loud_white":
+        snip = _coloured_noise(rng, m, 0.0, 1500.0)
+        pcm = _coloured_noise(rng, n, 0.0, 6000.0)                          # stream RMS = 4 x snippet RMS
+    elif kind == "coloured":
+        snip = _coloured_noise(rng, m, 0.97, 2500.0)
+        pcm = _coloured_noise(rng, n, 0.97, 7000.0)
+    else:
+        t = np.arange(n)
+        snip = np.round(3000 * np.sin(2 * np.pi * 440.0 / sr * np.arange(m)) + 300 * rng.standard_normal(m)).astype(np.int16)
+        pcm = np.round(6000 * np.sin(2 * np.pi * 440.0 / sr * t + 0.3) + 2000 * np.sin(2 * np.pi * 97.0 / sr * t)
+                       + 500 * rng.standard_normal(n)).astype(np.int16)
+    for k, o in enumerate([11003, 100000, 170500, 290001]):                # real occurrences on top of the programme
+        seg = pcm[o:o + m].astype(np.int32) // 2 + snip.astype(np.int32) * (2 if k % 2 == 0 else 1)
+        pcm[o:o + m] = np.clip(seg, -32768, 32767).astype(np.int16)
+    x, s = orc.pcm16_to_f32(pcm), orc.pcm16_to_f32(snip)
+    for dist, prom in ((480.0, 0.13), (1.0, 0.13), (3.0, 0.5)):
+        ref = orc.calc_chunks(x, s, sr, orc.make_config(5.0, m / sr, dist, prom), scale=True, precision=64, cap=1 << 18)
+        assert len(ref) >= 2                                                # (the global neighbour filter thins them at distance 480 s)
+        for log2 in (20, 15):
+            conf = am.Config(chunk_size=5.0, peak_config=am.PeakConfig(dist, prom), fft_log2=log2)
+            algo = am.CudaConvolve(snip, sr=sr, config=conf)
+            got = am.calc_chunks(sr, pcm, algo, True, conf, cap=1 << 18)
+            st = algo.stats()
+            algo.close()
+            assert (st["summary_mode"] != 0) == (log2 == 20), st
+            _assert_peaks(got, [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+
+
+@pytest.mark.parametrize("seed,dist,prom,maxpk", [(1, 0.0, 0.09, 0), (2, 1.0, 0.09, 32), (3, 3.0, 0.11, 0), (4, 480.0, 0.13, 8)])
 def test_calc_chunks_random_vs_oracle(am, orc, seed, dist, prom, maxpk):
     sr = 8000
     pcm = orc.synth_pcm16(1000 + seed, 0, sr * 33 + 17 * seed)             # ragged tail window
@@ -364,6 +415,49 @@ def test_progress_callback_and_shard_geometry(am, orc):
     algo.close()
 
 
+@pytest.mark.parametrize("piece", [1152, 100_003, 9_000_000])
+def test_push_session_equals_one_shot(am, orc, native, piece):
+    """am_stream_begin / push / finish (the lazy sample iterator of mp3_reader.rs:13-66 feeding calc_chunks,
+    matcher/mod.rs:71-83): pieces of an MP3 frame (1152 samples), of an odd size and larger than a pinned slot, segments
+    forced small (AM_SEGMENT_MB is read per call) so that several segments, both device buffers and the ov-frame halo
+    copy are exercised; the claimed length may exceed the true one.  Must equal am_calc_chunks on the whole stream."""
+    sr, m = 8000, 4000
+    pcm, snip, planted = orc.synth_case(sr, 1503.7, 0.5, chunk_s=5.0, plant_period_s=61.0, plant_jitter_s=7.0)
+    conf = am.Config(chunk_size=5.0, peak_config=am.PeakConfig(2.0, 0.13))
+    algo = am.CudaConvolve(snip, sr=sr, config=conf)
+    default_segments = am.calc_chunks(sr, pcm, algo, True, conf)
+    assert len(default_segments) > 10
+    os.environ["AM_SEGMENT_MB"] = "3"                                      # 3 MB of correlation per segment: ~18 chunks
+    try:
+        whole = am.calc_chunks(sr, pcm, algo, True, conf)                  # same segments => same block tiling => identical bits
+        assert [p.position.start for p in whole] == [p.position.start for p in default_segments]
+        for claimed in (len(pcm), len(pcm) + 12345):
+            got = am.calc_chunks_streamed(sr, (pcm[i:i + piece] for i in range(0, len(pcm), piece)), claimed, algo, True, conf)
+            assert [(p.position.start, p.position.stop, p.height, p.prominence, p.chunk) for p in got] == \
+                   [(p.position.start, p.position.stop, p.height, p.prominence, p.chunk) for p in whole]
+        st = algo.stats()
+        assert st["h2d_bytes"] >= 2 * len(pcm) and st["chunks"] == algo.num_chunks(len(pcm))
+        # stereo and f32 sessions, a session on a stream shorter than the snippet, misuse
+        stereo = np.stack([pcm, pcm], axis=1)
+        got = am.calc_chunks_streamed(sr, (stereo[i:i + 70001] for i in range(0, len(stereo), 70001)), len(stereo), algo, True, conf,
+                                      fmt=native.FMT_I16_STEREO)
+        assert [p.position.start for p in got] == [p.position.start for p in whole]
+        x = orc.pcm16_to_f32(pcm)
+        got = am.calc_chunks_streamed(sr, (x[i:i + 333333] for i in range(0, len(x), 333333)), len(x), algo, True, conf, fmt=native.FMT_F32_MONO)
+        assert [p.position.start for p in got] == [p.position.start for p in whole]
+        assert am.calc_chunks_streamed(sr, [pcm[:1000]], 1000, algo, True, conf) == []
+        sess = am.StreamSession(algo, 5000)
+        with pytest.raises(native.NativeError):
+            am.calc_chunks(sr, pcm, algo, True, conf)                       # the handle is busy with the session
+        with pytest.raises(native.NativeError):
+            sess.push(pcm[:6000])                                          # more than announced
+        sess.abort()
+        assert [p.position.start for p in am.calc_chunks(sr, pcm, algo, True, conf)] == [p.position.start for p in whole]
+    finally:
+        os.environ.pop("AM_SEGMENT_MB", None)
+        algo.close()
+
+
 def _peaks_from_correlation(am, native, c, m, C_, ov, prom, dist, summary, maxpk=0):
     """tests-only hook: per-chunk peak kernels on a supplied correlation (sr = 1, so seconds == samples)."""
     conf = am.Config(chunk_size=float(C_), overlap_length=float(ov), peak_config=am.PeakConfig(float(dist), prom),
@@ -413,9 +507,9 @@ def test_peak_kernels_on_adversarial_correlations(am, orc, native, seed, summary
     c[3 * C_ + 1023:3 * C_ + 1026] = 0.65                             # plateau across a tile boundary
     c[4 * C_:4 * C_ + 300] = np.linspace(0.0, 0.17, 300)              # monotone stretch
     c = c.astype(np.float32)
-    for prom, dist in ((0.13, 0), (0.25, 100), (0.13, 3000)):
+    for prom, dist, maxpk in ((0.13, 0, 4000), (0.25, 100, 4000), (0.13, 3000, 4000), (0.13, 1000, 24), (0.25, 3000, 8), (0.13, 400, 64)):   # small caps: many height bands
         ref = _oracle_peaks_from_correlation(orc, c, m, C_, ov, prom, dist)
-        got, mode = _peaks_from_correlation(am, native, c, m, C_, ov, prom, dist, summary, maxpk=4000)
+        got, mode = _peaks_from_correlation(am, native, c, m, C_, ov, prom, dist, summary, maxpk=maxpk)
         assert mode == (1 if summary else 0)
         assert len(ref) > 5
         assert sorted(got) == sorted(ref)
@@ -436,6 +530,11 @@ def test_peak_kernels_summary_rejections(am, orc, native):
     ref = _oracle_peaks_from_correlation(orc, c2, m, C_, m, 0.13, 0)
     got, mode = _peaks_from_correlation(am, native, c2, m, C_, m, 0.13, 0, 1, maxpk=4000)
     assert mode == 2 and sorted(got) == sorted(ref)
+    # with a minimum distance that one kept peak per chunk satisfies, the same data stays in summary mode: the kept
+    # peaks of height >= theta cover their chunks, whatever hides below theta cannot survive
+    ref = _oracle_peaks_from_correlation(orc, c2, m, C_, m, 0.13, 2 * C_)
+    got, mode = _peaks_from_correlation(am, native, c2, m, C_, m, 0.13, 2 * C_, 1)
+    assert mode == 1 and sorted(got) == sorted(ref)
 
 
 def test_edge_cases(am, orc, native):
@@ -573,18 +672,19 @@ def test_host_memory_path_equals_device_path(am, orc, full_size):
     assert [(p.position.start, p.height, p.prominence) for p in c] == [(p.position.start, p.height, p.prominence) for p in a]
 
 
-@pytest.mark.parametrize("env", [{"AM_COL_STREAM": "0"}, {"AM_ROW_STREAM": "1"}, {"AM_ROW_STREAM": "0"}])
+@pytest.mark.parametrize("env", [{"AM_COL_STREAM": "0"}, {"AM_ROW_STREAM": "1"}, {"AM_ROW_STREAM": "0"}, {"AM_BATCH_SNIPPETS": "3"}])
 def test_alternate_kernel_paths(env):
     """The kernel choices are read once per process; the non-default ones (plain-grid forward column kernel that also
     serves windows TMA cannot describe, persistent fused row kernel, plain inverse-only row kernel of batch mode) get
-    the correlation / golden / batch / full-size-vs-oracle tests in a child process."""
+    the correlation / golden / batch / full-size-vs-oracle tests in a child process; so does a batch whose snippet count
+    is not a multiple of the snippets per inverse-row launch."""
     if os.environ.get("AM_ALT_PATH_CHILD"):
         pytest.skip("child run")
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     child = dict(os.environ, AM_ALT_PATH_CHILD="1", **env)
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-x", "-q", "-m", "gpu",
-                          "-k", "correlate_vs_oracle or golden_cases or batch_equals or full_size_chunks_vs_oracle"],
+                          "-k", "correlate_vs_oracle or golden_cases or batch_equals or batch_of_8 or full_size_chunks_vs_oracle"],
                          cwd=root, env=child, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
 

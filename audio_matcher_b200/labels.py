@@ -9,6 +9,7 @@
 from __future__ import annotations
 
 from dataclasses import dataclass
+import numpy as np
 from pathlib import Path
 from typing import Iterable, Sequence
 
@@ -43,7 +44,11 @@ def offset_lines(peaks: Sequence, sr: int) -> list[str]:
     out = []
     for i, p in enumerate(peaks, start=1):
         secs = int(start_as_duration(p, sr))
-        out.append(f"Offset {i}: {secs // 3600:0>2}:{(secs // 60) % 60:0>2}:{secs % 60:0>2} with prominence {p.prominence}")
+        # Rust's `{}` on an f32: the shortest decimal that round-trips, never in exponent form (0.98765433, not the
+        # 0.9876543283462524 of the widened double).  hours()/minutes()/seconds() come from the private `common`
+        # crate: read here as hh of the total, mm and ss within the hour / minute (unpinned).
+        prom = np.format_float_positional(np.float32(p.prominence), unique=True, trim="-")
+        out.append(f"Offset {i}: {secs // 3600:0>2}:{(secs // 60) % 60:0>2}:{secs % 60:0>2} with prominence {prom}")
     return out
 
 

@@ -196,11 +196,18 @@ def with_tlen_seconds(data: bytes, seconds: int) -> bytes:
 
 
 # ---------------------------------------------------------------------------------------------- the function
-def mp3_duration(path, use_parallel: bool = False, cache: bool = True) -> float:
-    """mp3_reader.rs:68-108: seconds from the tag if it has a length, else from the frames -- then cached in the tag.
-
-    `use_parallel` is accepted for signature parity (the reference's rayon variant computes the same sum).
-    `cache=False` skips the write-back (the reference always writes)."""
+def mp3_duration(path, use_parallel: bool = False, header_walk_ok: bool = True, cache: bool = True) -> float:
+    """mp3_reader.rs:68-108, three steps:
+      1. the tag's length if it has one (whole seconds, tagger.rs:176-178)                                   :71-75
+      2. else the `mp3-duration` crate's walk over the frame headers -- NOTHING is written                   :76-79
+      3. only if both fail: the sum over the decoded frames, which is then cached in the tag as TLEN = whole
+         seconds (so every later call answers step 1 with the truncated value)                               :80-106
+    This mirror has one frame walk (`frame_walk`) standing in for both the crate (step 2) and the decoder sum
+    (step 3), which count the same samples on a well-formed stream.  An ordinary MP3 therefore returns its exact
+    duration and is never modified.  `header_walk_ok=False` reproduces the case where the crate gives up and the
+    reference falls through to step 3, the only path that rewrites the input file (source of the `ov < m - 1`
+    quirk); `cache=False` suppresses even that write.
+    `use_parallel` is accepted for signature parity (the reference's rayon variant computes the same sum)."""
     del use_parallel
     try:
         with open(path, "rb") as f:
@@ -211,6 +218,8 @@ def mp3_duration(path, use_parallel: bool = False, cache: bool = True) -> float:
     if tagged is not None:
         return float(tagged)
     seconds, _, _ = frame_walk(data)
+    if header_walk_ok:
+        return seconds
     if cache:
         try:
             image = with_tlen_seconds(data, int(seconds))

@@ -1,12 +1,17 @@
 //! Drop-in `CorrelateAlgo` / `calc_chunks` for NilsJochem/audio-matcher backed by libaudio_matcher_b200.so.
 //!
-//! Put this file at `src/matcher/cuda_convolve.rs` of the reference crate, add `pub mod cuda_convolve;` to
-//! `src/matcher/mod.rs`, link with `-l audio_matcher_b200`, and swap the two names in `matcher::run`
-//! (`src/matcher/mod.rs:34,81`).  It binds exactly the entry points declared in `include/audio_matcher.h`.
-//! Shipped as source: the build image has no Rust toolchain.
+//! Where it goes: `src/matcher/audio_matcher/cuda_convolve.rs`, declared as `pub mod cuda_convolve;` INSIDE
+//! `src/matcher/audio_matcher.rs` -- a child module may read the private fields of `Config` / `PeakConfig`
+//! (audio_matcher.rs:24-35), so the reference's types need no new getters.  Link with `-l audio_matcher_b200` and
+//! swap two names in `matcher::run` (src/matcher/mod.rs:34,81), see INTEGRATION.md.
+//! It binds entry points declared in `include/audio_matcher.h` and nothing else.
+//!
+//! UNTESTED SOURCE: the build image has no Rust toolchain (no cargo / rustc) and the crate's four private git
+//! dependencies are unreachable, so this file has never been compiled.  The same ABI calls, in the same order, are
+//! exercised from C (`tests/capi_smoke.c`), C++ (`include/audio_matcher.hpp`) and Python (`audio_matcher_b200`).
 use std::{ffi::CStr, os::raw::{c_char, c_int, c_void}, ptr};
 
-use crate::matcher::audio_matcher::{Config, CorrelateAlgo, Mode};
+use super::{Config, CorrelateAlgo, Mode};
 use crate::matcher::mp3_reader::SampleType;
 
 #[repr(C)]
@@ -38,10 +43,12 @@ pub struct AmPeak {
 pub struct AmMatcher {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct AmStreamSession {
+    _private: [u8; 0],
+}
 
 pub const AM_FMT_F32_MONO: c_int = 0;
-pub const AM_FMT_I16_MONO: c_int = 1;
-pub const AM_FMT_I16_STEREO: c_int = 2;
 pub const AM_MEM_HOST: c_int = 0;
 
 #[link(name = "audio_matcher_b200")]
@@ -54,8 +61,10 @@ extern "C" {
     fn am_out_len(n: usize, m: usize, mode: c_int) -> usize;
     fn am_correlate(h: *mut AmMatcher, within: *const c_void, n: usize, fmt: c_int, within_mem: c_int, mode: c_int,
                     scale: c_int, out: *mut f32, cap: usize, out_mem: c_int, out_len: *mut usize) -> c_int;
-    fn am_calc_chunks(h: *mut AmMatcher, stream: *const c_void, frames: usize, fmt: c_int, mem: c_int, scale: c_int,
-                      out: *mut AmPeak, cap: usize, n_out: *mut usize) -> c_int;
+    fn am_stream_begin(h: *mut AmMatcher, max_frames: usize, fmt: c_int, scale: c_int, out: *mut *mut AmStreamSession) -> c_int;
+    fn am_stream_push(s: *mut AmStreamSession, pcm: *const c_void, frames: usize) -> c_int;
+    fn am_stream_finish(s: *mut AmStreamSession, out: *mut AmPeak, cap: usize, n_out: *mut usize) -> c_int;
+    fn am_stream_abort(s: *mut AmStreamSession);
 }
 
 fn last_error() -> Box<dyn std::error::Error> {
@@ -66,8 +75,10 @@ fn last_error() -> Box<dyn std::error::Error> {
 pub struct CudaConvolve {
     h: *mut AmMatcher,
     m: usize,
+    sr: u16,
 }
-// The handle is internally locked; calc_chunks shares `&algo` across rayon workers (audio_matcher.rs:114-122).
+// Every entry point of the library takes the handle's mutex (am_capi.cu), so a shared `&CudaConvolve` is safe to
+// use from the rayon workers of the reference's generic calc_chunks (audio_matcher.rs:114-122); calls serialise.
 unsafe impl Send for CudaConvolve {}
 unsafe impl Sync for CudaConvolve {}
 
@@ -79,7 +90,7 @@ impl CudaConvolve {
         if rc != 0 {
             return Err(last_error());
         }
-        Ok(Self { h, m: sample_data.len() })
+        Ok(Self { h, m: sample_data.len(), sr })
     }
 }
 
@@ -113,20 +124,54 @@ impl CorrelateAlgo<SampleType> for CudaConvolve {
     }
 }
 
-/// Same contract as `calc_chunks` (audio_matcher.rs:88-141): peaks sorted by start, neighbours within
-/// `distance` with a larger prominence removed.  `cfg` carries the four values of `Config`/`PeakConfig`
-/// (their fields are private in the reference: add getters or build `AmConfig` in `Config::from_args`).
-pub fn calc_chunks_cuda(m_samples: impl ExactSizeIterator<Item = SampleType>, algo: &CudaConvolve, scale: bool,
-                        cfg: AmConfig) -> Vec<find_peaks::Peak<SampleType>> {
-    let stream: Vec<f32> = m_samples.collect();
+/// `calc_chunks` (audio_matcher.rs:88-141) with the same parameter list, the algo fixed to `CudaConvolve`: peaks
+/// sorted by start, neighbours within `distance` with a larger prominence removed.  The iterator is not collected:
+/// its frames are pushed block by block (`am_stream_push`), so the GPU matches while the decoder behind the
+/// iterator (mp3_reader.rs:13-66) is still producing; `m_samples.len()` is the claimed length of `with_size`
+/// (mod.rs:78,83) and only has to be an upper bound.
+pub fn calc_chunks<Iter: ExactSizeIterator<Item = SampleType>>(
+    sr: u16,
+    m_samples: Iter,
+    algo_with_sample: &CudaConvolve,
+    scale: bool,
+    config: Config,
+) -> Vec<find_peaks::Peak<SampleType>> {
+    assert_eq!(sr, algo_with_sample.sr, "sample rate of the stream differs from the snippet's"); // CliError::SampleRateMismatch, mod.rs:72
+    let cfg = AmConfig {
+        chunk_size_s: config.chunk_size.as_secs_f64(),
+        overlap_s: config.overlap_length.as_secs_f64(),
+        distance_s: config.peak_config.distance.as_secs_f64(),
+        prominence: config.peak_config.prominence,
+        fft_log2: 0,
+        max_peaks_per_chunk: 0,
+        reserved: 0,
+    };
+    const BLOCK: usize = 1 << 20;
+    let mut block: Vec<SampleType> = Vec::with_capacity(BLOCK);
     let mut peaks = vec![AmPeak::default(); 1 << 16];
     let mut n = 0usize;
     unsafe {
-        assert_eq!(am_matcher_set_config(algo.h, &cfg), 0, "{}", last_error());
-        let rc = am_calc_chunks(algo.h, stream.as_ptr().cast(), stream.len(), AM_FMT_F32_MONO, AM_MEM_HOST,
-                                c_int::from(scale), peaks.as_mut_ptr(), peaks.len(), &mut n);
-        assert_eq!(rc, 0, "{}", last_error()); // the reference unwraps as well (audio_matcher.rs:122)
+        assert_eq!(am_matcher_set_config(algo_with_sample.h, &cfg), 0, "{}", last_error());
+        let mut session = ptr::null_mut();
+        let claimed = m_samples.len().max(1);
+        assert_eq!(am_stream_begin(algo_with_sample.h, claimed, AM_FMT_F32_MONO, c_int::from(scale), &mut session), 0, "{}", last_error());
+        let mut it = m_samples;
+        loop {
+            block.clear();
+            block.extend(it.by_ref().take(BLOCK));
+            if block.is_empty() {
+                break;
+            }
+            if am_stream_push(session, block.as_ptr().cast(), block.len()) != 0 {
+                am_stream_abort(session);
+                panic!("{}", last_error()); // the reference unwraps as well (audio_matcher.rs:122)
+            }
+        }
+        assert_eq!(am_stream_finish(session, peaks.as_mut_ptr(), peaks.len(), &mut n), 0, "{}", last_error());
     }
+    // find_peaks 0.1: `pub struct Peak<T> { pub position: Range<usize>, pub left_diff: T, pub right_diff: T,
+    // pub height: Option<T>, pub prominence: Option<T> }` (crate source is not in the reference tree; downstream code
+    // reads position.start and prominence.unwrap(): audio_matcher.rs:135,155, mod.rs:122,128, archive/data.rs:94)
     peaks[..n].iter().map(|p| find_peaks::Peak {
         position: p.start as usize..p.end as usize,
         left_diff: p.left_diff,
@@ -134,10 +179,4 @@ pub fn calc_chunks_cuda(m_samples: impl ExactSizeIterator<Item = SampleType>, al
         height: Some(p.height),
         prominence: Some(p.prominence),
     }).collect()
-}
-
-#[allow(dead_code)]
-fn _config_from(config: &Config, chunk_size_s: f64, overlap_s: f64, distance_s: f64, prominence: f32) -> AmConfig {
-    let _ = config;
-    AmConfig { chunk_size_s, overlap_s, distance_s, prominence, fft_log2: 0, max_peaks_per_chunk: 0, reserved: 0 }
 }

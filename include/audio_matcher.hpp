@@ -24,6 +24,7 @@
 // There is no CPU fallback: without a CUDA device construction throws.
 #pragma once
 
+#include <charconv>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -172,9 +173,13 @@ inline std::vector<std::string> offset_lines(const std::vector<Peak> &peaks, uin
     if (peaks.empty()) out.push_back("no offsets found");
     for (std::size_t i = 0; i < peaks.size(); ++i) {
         const unsigned long long secs = (unsigned long long)start_as_duration(peaks[i], sr);
-        char buf[160];
-        std::snprintf(buf, sizeof buf, "Offset %zu: %02llu:%02llu:%02llu with prominence %g", i + 1, secs / 3600, (secs / 60) % 60,
-                      secs % 60, (double)peaks[i].prominence.value_or(0.f));
+        // Rust's `{}` on an f32 prints the shortest decimal that round-trips, never in exponent form
+        char prom[64];
+        const auto r = std::to_chars(prom, prom + sizeof prom - 1, peaks[i].prominence.value_or(0.f), std::chars_format::fixed);
+        *r.ptr = 0;
+        char buf[224];
+        std::snprintf(buf, sizeof buf, "Offset %zu: %02llu:%02llu:%02llu with prominence %s", i + 1, secs / 3600, (secs / 60) % 60,
+                      secs % 60, prom);
         out.push_back(buf);
     }
     return out;

@@ -82,6 +82,8 @@ static void labels_and_offsets() {
     ASSERT(labels[1].start == 1010.0 && labels[1].end == 4000.0 && labels[1].name == "Segment 2");
     ASSERT(labels[0].line() == "28.000000\t1003.000000\tSegment 1");
     ASSERT(offset_lines(peaks, 100)[1] == "Offset 2: 00:16:43 with prominence 0.5");
+    ASSERT(offset_lines({peak(100, 0.98765432f)}, 100)[0] == "Offset 1: 00:00:01 with prominence 0.9876543");   // Rust `{}` on f32
+    ASSERT(offset_lines({peak(100, 1.0f)}, 100)[0] == "Offset 1: 00:00:01 with prominence 1");
     ASSERT(offset_lines({}, 100).size() == 1 && offset_lines({}, 100)[0] == "no offsets found");
     ASSERT(timelabel_from_peaks({peak(5, 1.f)}, 1).empty());
 }

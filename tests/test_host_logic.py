@@ -116,4 +116,26 @@ def test_labels():
     assert [(l.start, l.end, l.name) for l in labels] == [(28.0, 1003.0, "Segment 1"), (1010.0, 4000.0, "Segment 2")]
     assert am.write_labels(labels, None, dry_run=True).splitlines()[0] == "28.000000\t1003.000000\tSegment 1"
     assert offset_lines(peaks, 100)[1] == "Offset 2: 00:16:43 with prominence 0.5"   # mod.rs:110-125
+    import ctypes
+    f32 = ctypes.c_float(0.98765432).value                                               # what am_peak.prominence hands back
+    line = offset_lines([am.Peak(range(100, 101), 1.0, f32, 0.1, 0.1), am.Peak(range(5, 6), 1.0, 1.0, 0, 0), am.Peak(range(7, 8), 1.0, 2.5e-7, 0, 0)], 100)
+    assert line[0].endswith("with prominence 0.9876543")                              # Rust `{}` on f32: shortest round-trip
+    assert line[1].endswith("with prominence 1") and line[2].endswith("with prominence 0.00000025")
     assert offset_lines([], 100) == ["no offsets found"]
+
+
+def test_integration_doc_matches_the_shim():
+    """INTEGRATION.md shows the reference-side binding; it must be the shipped ffi/cuda_convolve.rs, not a variant, and
+    the shim must bind only symbols the header declares, with the reference's calc_chunks parameter list."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = open(os.path.join(root, "ffi", "cuda_convolve.rs")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = doc.split("<!-- BEGIN ffi/cuda_convolve.rs -->")[1].split("<!-- END ffi/cuda_convolve.rs -->")[0]
+    assert block.strip() == "```rust\n" + shim.strip() + "\n```"
+    header = open(os.path.join(root, "include", "audio_matcher.h")).read()
+    bound = re.findall(r"fn (am_\w+)\(", shim.split('extern "C" {')[1].split("}")[0])
+    assert len(bound) >= 10 and all(re.search(rf"\b{name}\(", header) for name in bound)
+    sig = re.search(r"pub fn calc_chunks<.*?>>\(\n(.*?)\n\) ->", shim, re.S).group(1)
+    assert [a.split(":")[0].strip() for a in sig.split(",") if a.strip()] == ["sr", "m_samples", "algo_with_sample", "scale", "config"]
+    assert "_config_from" not in shim

@@ -48,11 +48,17 @@ def test_frame_walk_counts_samples_like_the_decoder_sum():
 
 
 def test_tag_cache_turns_the_duration_into_whole_seconds(tmp_path):
-    """The quirk behind `ov < m - 1`: first call 7.34 s from the frames, then TLEN = 7 is
-    stored and every later call answers 7 s (tagger.rs:176-178, :193)."""
+    """An ordinary untagged MP3 answers from the frame headers and is NOT modified (mp3_reader.rs:76-79).  Only when
+    the header walk of the `mp3-duration` crate fails does the reference fall through to its decoder sum and cache the
+    result in the tag (:80-106) -- the quirk behind `ov < m - 1`: that call returns 7.34 s, then
+    TLEN = 7 is stored and every later call answers 7 s (tagger.rs:176-178, :193)."""
     p = tmp_path / "interlude.mp3"
-    p.write_bytes(_stream(281))
-    first = md.mp3_duration(p)
+    original = _stream(281)
+    p.write_bytes(original)
+    for _ in range(2):
+        assert abs(md.mp3_duration(p) - 281 * 1152 / 44100) < 1e-9 and p.read_bytes() == original
+    assert abs(md.mp3_duration(p, header_walk_ok=False, cache=False) - 281 * 1152 / 44100) < 1e-9 and p.read_bytes() == original
+    first = md.mp3_duration(p, header_walk_ok=False)
     assert abs(first - 281 * 1152 / 44100) < 1e-9
     data = p.read_bytes()
     assert data[:3] == b"ID3" and md.read_tlen_seconds(data) == 7
@@ -128,14 +134,15 @@ def test_mirror_on_the_reference_fixture(tmp_path):
     p = tmp_path / "copy.mp3"
     p.write_bytes(data)
     assert md.mp3_duration(p) == 7.0 and p.read_bytes() == data          # tagged: answered from the tag, file untouched
-    # drop the length from the tag -> the frames answer, and the answer is cached as whole seconds
+    # drop the length from the tag -> the frames answer; only the decoder-sum fallback caches it as whole seconds
     t = md._split_tag(data)
     frames_wo = [f for f in md._frames_of(t[2], t[0]) if f[0] != b"TLEN"]
     body = b"".join(fid + struct.pack(">I", len(pl)) + fl + pl for fid, fl, pl in frames_wo)
     room = g["id3_extent"] - 10
     stripped = b"ID3\x03\x00\x00" + md._to_synchsafe(room) + body + b"\x00" * (room - len(body)) + data[g["id3_extent"]:]
     p.write_bytes(stripped)
-    assert abs(md.mp3_duration(p) - g["seconds"]) < 1e-12
+    assert abs(md.mp3_duration(p) - g["seconds"]) < 1e-12 and p.read_bytes() == stripped      # step 2: exact, file untouched
+    assert abs(md.mp3_duration(p, header_walk_ok=False) - g["seconds"]) < 1e-12                # step 3: cached afterwards
     again = p.read_bytes()
     assert md.read_tlen_seconds(again) == 7 and again[g["id3_extent"]:] == data[g["id3_extent"]:] and len(again) == len(data)
     assert md.mp3_duration(p) == 7.0

@@ -1180,10 +1180,10 @@ static am_status compute_segment(am_matcher *h, const RangePlan &pl, const amk::
     const long long g0 = pl.C * i0, g1 = pl.seg_out_end(i0, i1);
     if (g1 <= g0) return AM_OK;
     const amp::RunRecs no_recs{nullptr};
-    TRY(run_correlation(h, sv, g0, g1, pl.log2n, pl.scale, h->d_c.p, (size_t)pl.seg_c_len, g0, 0, pl.S, sum ? pl.recs : no_recs, pl.theta));
     amp::ChunkGeom cg;
     cg.C = pl.C; cg.ov = pl.ov; cg.m = pl.m; cg.total = pl.L; cg.first_chunk = i0; cg.c_g0 = g0; cg.tiles_stride = (int)pl.tiles_stride;
     cg.c_stride = pl.seg_c_len; cg.seg_end = g1 - g0;
+    TRY(run_correlation(h, sv, g0, g1, pl.log2n, pl.scale, h->d_c.p, (size_t)pl.seg_c_len, g0, 0, pl.S, sum ? pl.recs : no_recs, pl.theta));
     dim3 tgrid3((unsigned)((pl.tiles_stride + 7) / 8), (unsigned)(i1 - i0), (unsigned)pl.S), pgrid((unsigned)(i1 - i0), (unsigned)pl.S);
     if (sum) {
         LAUNCH(h, AM_K_TILE_MINMAX, amp::k_tile_from_runs<<<tgrid3, 256, 0, h->stream>>>(pl.recs, cg, h->d_tmin.p, h->d_tmax.p, pl.po));

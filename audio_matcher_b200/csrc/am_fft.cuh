@@ -361,6 +361,32 @@ template <int LOG2N, int LOG2B, bool INV, int E = EPT> struct RegFFT {
             dft<R, INV>(&v[l * R]);
         }
     }
+    // Stage 0 with an arbitrary multiplier per register, v[j] *= mul(j) (the snippet-spectrum product of the row pass
+    // rides on the first inverse butterflies: 28 instead of 32 instructions per 4-point group, and the multipliers
+    // are consumed group by group while later ones are still in flight)
+    template <class Mul> static AM_HD void butterfly0_mul(float2 (&v)[EPT], Mul &&mul) {
+        constexpr int RB = bits_at(0), R = 1 << RB, NB = EPT / R;
+#ifndef AM_FFT_LEGACY
+        if constexpr (R == 16) {
+#pragma unroll
+            for (int n2 = 0; n2 < 4; ++n2) {
+#pragma unroll
+                for (int f = 0; f < NB; ++f) {
+                    float2 *x = &v[16 * f];
+                    x[n2] = cmul(x[n2], mul(16 * f + n2));
+                    dft4_tw<INV>(x[n2], x[4 + n2], x[8 + n2], x[12 + n2], mul(16 * f + 4 + n2), mul(16 * f + 8 + n2), mul(16 * f + 12 + n2));
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < NB; ++f) dft16_layer2<INV>(&v[16 * f]);
+            return;
+        }
+#endif
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) v[j] = cmul(v[j], mul(j));
+#pragma unroll
+        for (int l = 0; l < NB; ++l) dft<R, INV>(&v[l * R]);
+    }
     // Stage 0 with geometric input twiddles v[l R + r] *= base[l] step^r (the four-step twiddles of the inverse
     // column pass ride on the first butterflies)
     static AM_HD void butterfly0_geo(float2 (&v)[EPT], const float2 *base, float2 step) {

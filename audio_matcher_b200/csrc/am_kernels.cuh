@@ -709,18 +709,26 @@ k_row32(float2 *__restrict__ A, const float2 *__restrict__ spec, float2 *__restr
         }
     }
     const float2 *Sr = spec + ((size_t)(row & ((1 << log2n1) - 1)) << L2);
+    if constexpr (MODE == ROW_INVERSE) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        int idx, t;
-        I::template in_coord<0>(gtid, j, idx, t);            // == F::out_coord: no exchange across the multiply
-        if constexpr (MODE == ROW_INVERSE) v[j] = Ar[idx];
-        v[j] = amfft::cmul(v[j], __ldg(&Sr[idx]));
+        for (int j = 0; j < 32; ++j) {
+            int idx, t;
+            I::template in_coord<0>(gtid, j, idx, t);
+            v[j] = Ar[idx];
+        }
     }
+    // the product with the conjugate snippet spectrum rides on the first inverse butterflies; register j holds
+    // element I::in_coord<0>(j) == F::out_coord(j): no exchange across the multiply
+    I::butterfly0_mul(v, [&](int j) {
+        int idx, t;
+        I::template in_coord<0>(gtid, j, idx, t);
+        return __ldg(&Sr[idx]);
+    });
     AM_TL_WAIT(v, 32);
     AM_TL(3);
     // fused: the forward transform's last exchange reads must be over before the inverse writes (barrier after the
     // first inverse butterflies); nothing touches the buffer after the inverse
-    I::template run<0, false, MODE == ROW_FUSED>(v, sm, gtid, tw);
+    I::template run<0, false, MODE == ROW_FUSED, true>(v, sm, gtid, tw);
     AM_TL(4);
     float2 *Or = (MODE == ROW_INVERSE) ? Bout + ((size_t)row << L2) : Ar;
 #pragma unroll

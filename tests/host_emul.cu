@@ -176,6 +176,44 @@ template <int LOG2N, int LOG2B, int E> static double check_geo() {
     return rel;
 }
 
+// stage 0 with one multiplier per register (RegFFT::butterfly0_mul, the spectrum product of the row pass)
+template <int LOG2N, int E> static double check_mul() {
+    typedef RegFFT<LOG2N, 0, true, E> F;
+    constexpr int N = F::N, GT = F::GT, EPT = E;
+    std::vector<float2> x(N), w(N);
+    for (auto &e : x) e = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+    for (auto &e : w) e = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+    std::vector<float2> regs(GT * EPT), sm(F::SMEM_ELEMS, make_float2(NAN, NAN));
+    for (int t = 0; t < GT; ++t) {
+        for (int j = 0; j < EPT; ++j) {
+            int idx, c;
+            F::template in_coord<0>(t, j, idx, c);
+            regs[t * EPT + j] = x[idx];
+        }
+        F::butterfly0_mul(*(float2(*)[EPT]) & regs[t * EPT], [&](int j) {
+            int idx, c;
+            F::template in_coord<0>(t, j, idx, c);
+            return w[idx];
+        });
+    }
+    RunnerFrom1<F, 0>::go(regs, sm);
+    std::vector<cd> a(N);
+    for (int i = 0; i < N; ++i) a[i] = cd(x[i].x, x[i].y) * cd(w[i].x, w[i].y);
+    ref_fft(a, true);
+    double maxerr = 0, maxref = 0;
+    for (int t = 0; t < GT; ++t)
+        for (int j = 0; j < EPT; ++j) {
+            int idx, c;
+            F::out_coord(t, j, idx, c);
+            double e = std::abs(a[idx] - cd(regs[t * EPT + j].x, regs[t * EPT + j].y));
+            if (!(e <= maxerr)) maxerr = e;
+            maxref = std::max(maxref, std::abs(a[idx]));
+        }
+    double rel = maxerr / maxref;
+    printf("multiplied stage 0: log2n=%d ept=%d  max_rel_err=%.3g %s\n", LOG2N, E, rel, rel < 2e-6 ? "OK" : "FAIL");
+    return rel;
+}
+
 int main() {
     g_tw.resize(TW_N);
     for (int j = 0; j < TW_N; ++j) {
@@ -196,6 +234,10 @@ int main() {
     worst = std::max(worst, check_roundtrip<12, 32>());
     worst = std::max(worst, check_roundtrip<13, 32>());
     worst = std::max(worst, check_roundtrip<14, 32>());
+    worst = std::max(worst, check_mul<13, 32>());
+    worst = std::max(worst, check_mul<14, 32>());
+    worst = std::max(worst, check_mul<12, 32>());
+    worst = std::max(worst, check_mul<10, 16>());
     worst = std::max(worst, check_geo<9, 4, 32>());
     worst = std::max(worst, check_geo<9, 4, 16>());
     worst = std::max(worst, check_geo<10, 3, 16>());

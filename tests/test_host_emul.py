@@ -14,7 +14,7 @@ def test_register_fft_emulation(tmp_path):
     if not os.path.exists(nvcc) and not shutil.which("nvcc"):
         pytest.skip("nvcc not available")
     exe = tmp_path / "host_emul"
-    subprocess.run([nvcc, "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-o", str(exe),
+    subprocess.run([nvcc, "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-diag-suppress", "128,20011", "-o", str(exe),
                     os.path.join(ROOT, "tests", "host_emul.cu")], check=True, capture_output=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout[-2000:]

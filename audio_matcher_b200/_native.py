@@ -98,6 +98,7 @@ SYMBOLS = {
     "am_debug_peaks_from_correlation": (C.c_int, [_VP, _VP, _SZ, C.c_int, C.POINTER(AmPeak), _SZ, C.POINTER(_SZ),
                                                   C.POINTER(C.c_uint32)]),
     "am_synth_pcm16_device": (C.c_int, [C.c_uint64, C.c_uint64, _SZ, _VP, _VP]),
+    "am_synth_coloured_pcm16_device": (C.c_int, [C.c_uint64, C.c_uint64, _SZ, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     "am_synth_plant_device": (C.c_int, [_VP, _SZ, C.c_int, _VP, _SZ, C.c_uint64, C.c_int, _VP]),
 }
 

@@ -153,10 +153,11 @@ struct HostStager {
         }
     }
     void parallel_copy(void *dst, const void *src, size_t n) {
-        if (workers.empty() || n < ((size_t)2 << 20)) { memcpy(dst, src, n); return; }
+        if (workers.empty() || n < ((size_t)1 << 20)) { memcpy(dst, src, n); return; }
         std::unique_lock<std::mutex> lk(mu);
         job_dst = (char *)dst; job_src = (const char *)src; job_n = n;
-        job_piece = (size_t)1 << 20;
+        // two pieces per thread, between 128 KB and 1 MB each: a 4 MB push still keeps the whole pool busy
+        job_piece = std::min<size_t>((size_t)1 << 20, std::max<size_t>((size_t)128 << 10, (n / (2 * (workers.size() + 1)) + 4095) & ~(size_t)4095));
         job_pieces = (n + job_piece - 1) / job_piece;
         next_piece = 0; pieces_done = 0;
         ++generation;
@@ -769,6 +770,16 @@ __device__ __forceinline__ unsigned long long hash64(unsigned long long seed, un
 __global__ void k_synth_pcm16(unsigned long long seed, unsigned long long first, size_t count, short *out) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
         out[i] = (short)((int)(hash64(seed, first + i) >> 50) - 8192);
+}
+// coloured noise: a boxcar of `taps` white samples, scaled by mul / 2^shift (integer arithmetic only)
+__global__ void k_synth_coloured16(unsigned long long seed, unsigned long long first, size_t count, int taps, int mul, int shift,
+                                   short *out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        long long acc = 0;
+        for (int k = 0; k < taps; ++k) acc += (int)(hash64(seed, first + i - (unsigned long long)k) >> 50) - 8192;
+        long long v = (acc * mul) >> shift;
+        out[i] = (short)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v));
+    }
 }
 __global__ void k_synth_plant(short *pcm, size_t frames, int channels, const short *snip, size_t m,
                               unsigned long long offset, int shift) {
@@ -1828,6 +1839,15 @@ am_status am_synth_pcm16_device(uint64_t seed, uint64_t first, size_t count, int
     if (!dev_out) return fail(AM_ERR_INVALID, "NULL buffer");
     unsigned grid = (unsigned)std::min<size_t>((count + 255) / 256, 148 * 32);
     k_synth_pcm16<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(seed, first, count, dev_out);
+    CU(cudaGetLastError());
+    return AM_OK;
+}
+am_status am_synth_coloured_pcm16_device(uint64_t seed, uint64_t first, size_t count, int taps, int mul, int shift,
+                                         int16_t *dev_out, void *cuda_stream) {
+    if (count == 0) return AM_OK;
+    if (!dev_out || taps < 1 || taps > 4096 || shift < 0 || shift > 30) return fail(AM_ERR_INVALID, "bad argument");
+    unsigned grid = (unsigned)std::min<size_t>((count + 255) / 256, 148 * 32);
+    k_synth_coloured16<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(seed, first, count, taps, mul, shift, dev_out);
     CU(cudaGetLastError());
     return AM_OK;
 }

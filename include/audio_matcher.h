@@ -242,6 +242,10 @@ am_status am_debug_peaks_from_correlation(am_matcher *h, const float *c_host, si
  * Device-side, integer-only, bit-identical to the oracle's generator.
  * out[i] = int16((hash64(seed, first + i) >> 50) - 8192) */
 am_status am_synth_pcm16_device(uint64_t seed, uint64_t first, size_t count, int16_t *dev_out, void *cuda_stream);
+/* coloured (low-pass) noise for the loud / coloured-programme bench legs:
+ * out[i] = sat16((sum_{k < taps} (int16((hash64(seed, first + i - k) >> 50) - 8192)) * mul) >> shift) */
+am_status am_synth_coloured_pcm16_device(uint64_t seed, uint64_t first, size_t count, int taps, int mul, int shift,
+                                         int16_t *dev_out, void *cuda_stream);
 /* x[(offset + j)*channels + c] = sat16((x >> 1) + (snip[j] >> shift)), j < m, frame < frames */
 am_status am_synth_plant_device(int16_t *dev_pcm, size_t frames, int channels, const int16_t *dev_snip, size_t m,
                                 uint64_t offset, int shift, void *cuda_stream);

@@ -1743,6 +1743,10 @@ am_status am_comm_init(int nranks, int rank, const void *nccl_unique_id, am_comm
     if (!c) return fail(AM_ERR_NOMEM, "out of host memory");
     c->nranks = nranks;
     c->rank = rank;
+    if (const char *v = getenv("AM_GATHER_RECORD_PEAKS")) {      // tests: a tiny record forces the second all-gather round
+        const long long x = atoll(v);
+        if (x > 0) c->record_peaks = (size_t)x;
+    }
     cudaError_t e = cudaGetDevice(&c->device);
     if (e != cudaSuccess) { delete c; return fail(AM_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e)); }
     NcclId id;

@@ -7,6 +7,11 @@
 #include <stdlib.h>
 #include "audio_matcher.h"
 
+static void progress_cb(void *user, int phase, size_t first_chunk, size_t n_chunks) {
+    (void)first_chunk;
+    if (phase == 1) *(size_t *)user += n_chunks;             /* phase 1: the peaks of the call are final */
+}
+
 int main(void) {
     if (am_abi_version() != AM_ABI_VERSION) { fprintf(stderr, "ABI version mismatch\n"); return 2; }
     if (am_device_count() < 1) { fprintf(stderr, "no CUDA device: %s\n", "cannot run"); return 77; }
@@ -46,6 +51,34 @@ int main(void) {
         fabsf(peaks[1].prominence - 1.0f) > 1e-6f || fabsf(peaks[2].prominence - 0.3f) > 1e-6f ||
         fabsf(peaks[0].prominence - 0.2f) > 1e-6f) {
         fprintf(stderr, "find_peaks KAT failed (%zu peaks)\n", n);
+        return 1;
+    }
+    /* the same through a push session (the lazy sample iterator of mp3_reader.rs:13-66): three pieces, claimed length 9 */
+    static size_t seen_chunks;
+    seen_chunks = 0;
+    if (am_matcher_set_progress(g, progress_cb, &seen_chunks) != AM_OK) { fprintf(stderr, "set_progress: %s\n", am_last_error()); return 1; }
+    am_stream_session *s = NULL;
+    if (am_stream_begin(g, 9, AM_FMT_F32_MONO, 1, &s) != AM_OK) { fprintf(stderr, "stream_begin: %s\n", am_last_error()); return 1; }
+    if (am_calc_chunks(g, y, 7, AM_FMT_F32_MONO, AM_MEM_HOST, 1, peaks, 8, &n) != AM_ERR_INVALID) { fprintf(stderr, "busy handle not reported\n"); return 1; }
+    if (am_stream_push(s, y, 2) != AM_OK || am_stream_push(s, y + 2, 4) != AM_OK || am_stream_push(s, y + 6, 1) != AM_OK) {
+        fprintf(stderr, "stream_push: %s\n", am_last_error());
+        return 1;
+    }
+    am_peak streamed[8];
+    size_t ns = 0;
+    if (am_stream_finish(s, streamed, 8, &ns) != AM_OK) { fprintf(stderr, "stream_finish: %s\n", am_last_error()); return 1; }
+    if (ns != 3 || streamed[0].start != 1 || streamed[1].start != 3 || streamed[2].start != 5 || streamed[1].prominence != peaks[1].prominence) {
+        fprintf(stderr, "push session differs from the one-shot call (%zu peaks)\n", ns);
+        return 1;
+    }
+    if (seen_chunks != 1) { fprintf(stderr, "progress callback saw %zu chunks\n", seen_chunks); return 1; }
+    /* chunk geometry and shard frames as the library rounds them (audio_matcher.rs:99-100) */
+    size_t C = 0, ov = 0, lo = 0, hi = 0;
+    if (am_chunk_geometry(g, &C, &ov) != AM_OK || C != 7 || ov != 0) { fprintf(stderr, "chunk geometry %zu %zu\n", C, ov); return 1; }
+    if (am_shard_frames(g, 100, 3, 2, &lo, &hi) != AM_OK || lo != 21 || hi != 35) { fprintf(stderr, "shard frames %zu %zu\n", lo, hi); return 1; }
+    /* one rank is a valid communicator-less call of the sharded entry point */
+    if (am_calc_chunks_sharded(g, NULL, y, 0, 7, 7, AM_FMT_F32_MONO, AM_MEM_HOST, 1, 0, 1, peaks, 8, &n) != AM_OK || n != 3) {
+        fprintf(stderr, "calc_chunks_sharded: %s\n", am_last_error());
         return 1;
     }
     am_matcher_destroy(g);

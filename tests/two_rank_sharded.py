@@ -17,38 +17,47 @@ import audio_matcher_b200 as am  # noqa: E402
 from audio_matcher_b200.matcher import shard_chunks  # noqa: E402
 from oracle import am_oracle as orc  # noqa: E402  (checker)
 
-if rank == 0:
-    uid = am.Comm.unique_id()
-    with open(id_file + ".tmp", "wb") as f:
-        f.write(uid)
-    os.replace(id_file + ".tmp", id_file)
-else:
-    t0 = time.time()
-    while not os.path.exists(id_file):
-        if time.time() - t0 > 120:
-            raise SystemExit("no unique id file")
-        time.sleep(0.05)
-    with open(id_file, "rb") as f:
-        uid = f.read()
-comm = am.Comm(nranks, rank, uid)
+def make_comm(tag):
+    """Rank 0 creates the unique id and publishes it in a file; the others poll for it."""
+    path = f"{id_file}.{tag}"
+    if rank == 0:
+        uid = am.Comm.unique_id()
+        with open(path + ".tmp", "wb") as f:
+            f.write(uid)
+        os.replace(path + ".tmp", path)
+    else:
+        t0 = time.time()
+        while not os.path.exists(path):
+            if time.time() - t0 > 120:
+                raise SystemExit("no unique id file")
+            time.sleep(0.05)
+        with open(path, "rb") as f:
+            uid = f.read()
+    return am.Comm(nranks, rank, uid)
+
 
 sr, chunk_s, dist_s = 8000, 5.0, 12.0
 pcm, snip, planted = orc.synth_case(sr, 83.0, 0.5, chunk_s=chunk_s, plant_period_s=12.5, plant_jitter_s=2.5)
+x, s = orc.pcm16_to_f32(pcm), orc.pcm16_to_f32(snip)
+ref = orc.calc_chunks(x, s, sr, orc.make_config(chunk_s, len(s) / sr, dist_s, 0.13), scale=True, precision=64)
+assert len(ref) >= 3, ref
 conf = am.Config(chunk_size=chunk_s, peak_config=am.PeakConfig(dist_s, 0.13))
 algo = am.CudaConvolve(snip, sr=sr, config=conf)
 total = algo.num_chunks(len(pcm))
 c0, nc = shard_chunks(total, nranks, rank)
 lo, hi = algo.shard_frames(c0, nc, len(pcm))
-for samples in (np.ascontiguousarray(pcm[lo:hi]),):                       # host shard; the device path is the bench's
-    got = algo.calc_chunks_sharded(samples, True, total_frames=len(pcm), buf_first_frame=lo, first_chunk=c0, num_chunks=nc, comm=comm)
-    x, s = orc.pcm16_to_f32(pcm), orc.pcm16_to_f32(snip)
-    ref = orc.calc_chunks(x, s, sr, orc.make_config(chunk_s, len(s) / sr, dist_s, 0.13), scale=True, precision=64)
-    assert len(ref) >= 3, ref
-    assert [(p.position.start, p.position.stop, p.chunk) for p in got] == [(p.start, p.end, p.chunk) for p in ref], (got, ref)
-    for a, b in zip(got, ref):
-        assert abs(a.height - b.height) <= 1e-4 * abs(b.height) and abs(a.prominence - b.prominence) <= 1e-4 * abs(b.prominence)
-# a tiny record capacity forces the second all-gather round (a rank with more peaks than the record holds)
-import ctypes as C  # noqa: E402
+shard = np.ascontiguousarray(pcm[lo:hi])
+# second pass: a record of 1 peak per rank cannot hold a shard's peaks -> the library has to gather a second time
+for tag, record in (("a", None), ("b", "1")):
+    if record:
+        os.environ["AM_GATHER_RECORD_PEAKS"] = record
+    comm = make_comm(tag)
+    os.environ.pop("AM_GATHER_RECORD_PEAKS", None)
+    for samples in (shard, __import__("torch").from_numpy(shard).cuda()):      # host shard and device-resident shard
+        got = algo.calc_chunks_sharded(samples, True, total_frames=len(pcm), buf_first_frame=lo, first_chunk=c0, num_chunks=nc, comm=comm)
+        assert [(p.position.start, p.position.stop, p.chunk) for p in got] == [(p.start, p.end, p.chunk) for p in ref], (got, ref)
+        for a, b in zip(got, ref):
+            assert abs(a.height - b.height) <= 1e-4 * abs(b.height) and abs(a.prominence - b.prominence) <= 1e-4 * abs(b.prominence)
+    comm.close()
 algo.close()
-comm.close()
 print(f"rank {rank}: sharded ok, {len(got)} peaks")

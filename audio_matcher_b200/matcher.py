@@ -380,6 +380,23 @@ def shard_frames(first_chunk: int, num_chunks: int, total_frames: int, sr: int, 
     return lo, hi
 
 
+def _preload_bundled_nccl() -> None:
+    """The library binds NCCL with dlopen("libnccl.so.2") and reuses a copy that is already mapped.  In a Python
+    process that will also import torch, the copy torch bundles (nvidia/nccl/lib) must be the one that gets mapped:
+    a system libnccl.so.2 loaded first would satisfy torch's own DT_NEEDED by soname and can be too old for it."""
+    import importlib.util
+    import os
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass                                    # no bundled copy: the library falls back to the system's libnccl.so.2
+
+
 class Comm:
     """am_comm: the NCCL communicator of the C ABI (one process per GPU).  `unique_id` is the 128-byte id rank 0
     got from Comm.unique_id(); how it reaches the other ranks is the caller's business."""
@@ -389,6 +406,7 @@ class Comm:
     def __init__(self, nranks: int, rank: int, unique_id: bytes):
         if len(unique_id) != N.COMM_ID_BYTES:
             raise ValueError("unique_id must be 128 bytes")
+        _preload_bundled_nccl()
         c = C.c_void_p()
         idbuf = C.create_string_buffer(bytes(unique_id), N.COMM_ID_BYTES)
         N.check(N.lib().am_comm_init(nranks, rank, idbuf, C.byref(c)))
@@ -397,6 +415,7 @@ class Comm:
 
     @staticmethod
     def unique_id() -> bytes:
+        _preload_bundled_nccl()
         buf = C.create_string_buffer(N.COMM_ID_BYTES)
         N.check(N.lib().am_comm_get_unique_id(buf))
         return buf.raw

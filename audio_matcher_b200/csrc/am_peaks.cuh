@@ -435,6 +435,11 @@ k_chunk_peaks(const float *__restrict__ c, RunRecs rsum, float theta, ChunkGeom 
     __syncthreads();
     const float cmin = s_cmin, gmax = s_gmax;
     if (!(gmax - cmin >= min_prom)) return;                         // no sample can reach the prominence: no peaks
+    // tiles that can hold a candidate: many of them means loud / coloured material where almost every local maximum
+    // passes the bound -- the descent then starts with a thin band under the chunk maximum instead of everything
+    int nq = 0;
+    for (long long t = tid; t < ntiles; t += 256) nq += (tmax[t] - cmin >= min_prom) ? 1 : 0;
+    const int many_tiles = __syncthreads_count(nq > 0 ? 1 : 0) > 16;   // (threads that saw a qualifying tile: > 16 <=> > 16 tiles)
     auto mark_dense = [&]() {                                       // this chunk is repeated on a dense correlation; emits nothing here
         if (tid == 0) { out.redo[ridx] = 1; atomicOr(out.flags, FLAG_NEED_DENSE); }
     };
@@ -543,6 +548,10 @@ k_chunk_peaks(const float *__restrict__ c, RunRecs rsum, float theta, ChunkGeom 
         const float top = (hi < CUDART_INF_F) ? hi : gmax;
         float lo = lo_floor;
         if (band > 0 && width > 0.f && hi - 2.f * width > b0) lo = hi - 2.f * width;
+        if (band == 0 && many_tiles && min_dist > 0) {
+            const float thin = gmax - (gmax - fmaxf(b0, cmin + min_prom)) * (1.0f / 64.0f);
+            if (thin > b0 && thin < gmax) lo = thin;
+        }
         int ncand = 0;
         for (;;) {
             __syncthreads();

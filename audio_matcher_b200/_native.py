@@ -26,7 +26,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "--expt-relaxed-constexpr", "-gencode", "arch
               "-lineinfo", "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "128", "-ldl"]
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t)
 COMM_ID_BYTES = 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class AmConfig(C.Structure):
@@ -90,6 +90,8 @@ SYMBOLS = {
     "am_calc_chunks_sharded": (C.c_int, [_VP, _VP, _VP, _SZ, _SZ, _SZ, C.c_int, C.c_int, C.c_int, _SZ, _SZ,
                                          C.POINTER(AmPeak), _SZ, C.POINTER(_SZ)]),
     "am_calc_chunks": (C.c_int, [_VP, _VP, _SZ, C.c_int, C.c_int, C.c_int, C.POINTER(AmPeak), _SZ, C.POINTER(_SZ)]),
+    "am_calc_chunks_files": (C.c_int, [_VP, _SZ, C.POINTER(_VP), C.POINTER(_SZ), C.c_int, C.c_int, C.c_int, C.POINTER(AmPeak), _SZ,
+                                       C.POINTER(_SZ)]),
     "am_calc_chunks_range": (C.c_int, [_VP, _VP, _SZ, _SZ, _SZ, C.c_int, C.c_int, C.c_int, _SZ, _SZ, C.c_int,
                                        C.POINTER(AmPeak), _SZ, C.POINTER(_SZ)]),
     "am_merge_peaks": (C.c_int, [C.POINTER(AmPeak), _SZ, C.c_uint32, C.c_double, C.POINTER(AmPeak), _SZ,

@@ -240,6 +240,11 @@ struct am_matcher {
     DevBuf<unsigned char> d_stage[2];
     HostStager stager;                      // pageable host streams only
     DevBuf<unsigned char> d_gsend, d_grecv; // multi-GPU: fixed-size peak records for the all-gather
+    // am_calc_chunks_files: per-file peak lists, counters and dense-repeat marks, so that the work of all files is
+    // queued before the first result is read back
+    DevBuf<amp::DevPeak> d_fpeaks;
+    DevBuf<unsigned long long> d_fcount;
+    DevBuf<unsigned char> d_fredo;
     bool in_session = false;                // a push session (am_stream_begin) owns the calc_chunks buffers
     am_progress_fn progress = nullptr;      // optional, fired from the calling thread
     void *progress_user = nullptr;
@@ -894,6 +899,7 @@ void am_matcher_destroy(am_matcher *h) {
     h->d_snip.release(); h->d_tw.release(); h->d_A.release(); h->d_B.release(); h->d_c.release(); h->d_tmin.release();
     h->d_tmax.release(); h->d_rsum.release(); h->d_peaks.release(); h->d_redo.release(); h->d_count.release(); h->d_sched.release();
     h->d_stage[0].release(); h->d_stage[1].release(); h->stager.release(); h->d_gsend.release(); h->d_grecv.release();
+    h->d_fpeaks.release(); h->d_fcount.release(); h->d_fredo.release();
     for (int i = 0; i < 2; ++i) {
         if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
@@ -1361,6 +1367,140 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
         if (!out) return fail(AM_ERR_INVALID, "NULL output buffer");
         memcpy(out, kept.data(), nk * sizeof(am_peak));
     }
+    return AM_OK;
+}
+
+// ---- several files per call ------------------------------------------------------------------------------
+// The reference matches its snippet against every file of args.within in turn (src/matcher/mod.rs:42-99), one
+// calc_chunks per file.  Here the transforms + peak kernels of ALL files are queued first -- each file with its own
+// peak list, counter and dense-repeat marks on the device -- and read back after one synchronisation: the upload of
+// file k+1 (copy stream, the other staging buffer) overlaps the kernels of file k, and short files do not drain
+// the GPU between calls.  A file whose run records cannot decide some chunk, or that outgrows its share of the
+// peak list, is repeated through the one-file path.  Results per file equal am_calc_chunks on that file.
+am_status am_calc_chunks_files(am_matcher *h, size_t n_files, const void *const *streams, const size_t *frames,
+                               am_sample_fmt fmt, am_mem mem, int scale, am_peak *out, size_t cap, size_t *n_out) {
+    if (!h || !n_out || (n_files && (!streams || !frames))) return fail(AM_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (size_t f = 0; f < n_files; ++f) n_out[f] = 0;
+    if (h->in_session) return fail(AM_ERR_INVALID, "a push session is open on this matcher");
+    if (n_files == 0) return AM_OK;
+    const size_t F = n_files, S = h->S;
+    size_t fmax = 0;
+    for (size_t f = 0; f < F; ++f) {
+        if (frames[f] && !streams[f]) return fail(AM_ERR_INVALID, "file %zu: NULL stream", f);
+        if (frames[f] > frames[fmax]) fmax = f;
+    }
+    // the longest file sizes the shared buffers once (a buffer that had to grow later would synchronise the device)
+    RangePlan plmax;
+    bool nothing = true;
+    TRY(plan_range(h, frames[fmax], fmt, mem == AM_MEM_HOST, scale, 0, (size_t)-1, plmax, &nothing));
+    if (!nothing && mem == AM_MEM_HOST) {
+        const size_t seg_bytes = (size_t)std::min<long long>(plmax.L, plmax.K * plmax.C + plmax.ov) * plmax.fb;
+        TRY(h->d_stage[0].reserve(seg_bytes));
+        if (F > 1 || (long long)plmax.num_chunks > plmax.K) TRY(h->d_stage[1].reserve(seg_bytes));
+    }
+    std::vector<size_t> pk_off(F + 1, 0), redo_off(F + 1, 0), pk_cap(F, 0);
+    const size_t per_chunk = h->cfg.max_peaks_per_chunk ? h->cfg.max_peaks_per_chunk : 1024;
+    const size_t min_cap = getenv("AM_FILES_MIN_CAP") ? env_mb("AM_FILES_MIN_CAP", 1) : 0;   // test knob: a file's share of the peak list
+    for (size_t f = 0; f < F; ++f) {
+        const size_t nc = am_num_chunks(h, frames[f]);
+        pk_cap[f] = std::min(nc * per_chunk * S, min_cap ? min_cap : std::max<size_t>(4096, 16 * nc * S));
+        pk_off[f + 1] = pk_off[f] + pk_cap[f];
+        redo_off[f + 1] = redo_off[f] + nc * S;
+    }
+    TRY(h->d_fpeaks.reserve(std::max<size_t>(pk_off[F], 1)));
+    TRY(h->d_fcount.reserve(2 * F));
+    TRY(h->d_fredo.reserve(std::max<size_t>(redo_off[F], 1)));
+    CU(cudaMemsetAsync(h->d_fcount.p, 0, 2 * F * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_fredo.p, 0, std::max<size_t>(redo_off[F], 1), h->stream));
+    int stage_threads = 0;
+    if (mem == AM_MEM_HOST && streams[fmax]) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, streams[fmax]) == cudaSuccess && pa.type == cudaMemoryTypeUnregistered) stage_threads = HostStager::default_threads();
+        cudaGetLastError();
+    }
+
+    // queue every file
+    am_stats acc;
+    memset(&acc, 0, sizeof acc);
+    std::vector<RangePlan> pls(F);
+    std::vector<char> queued(F, 0);
+    int seg_idx = 0;
+    for (size_t f = 0; f < F; ++f) {
+        RangePlan &pl = pls[f];
+        TRY(plan_range(h, frames[f], fmt, mem == AM_MEM_HOST, scale, 0, (size_t)-1, pl, &nothing));
+        if (nothing) continue;
+        queued[f] = 1;
+        pl.po.peaks = h->d_fpeaks.p + pk_off[f]; pl.po.cap = pk_cap[f]; pl.dev_cap = pk_cap[f];
+        pl.po.count = h->d_fcount.p + 2 * f; pl.po.flags = (unsigned *)(h->d_fcount.p + 2 * f + 1);
+        pl.po.redo = h->d_fredo.p + redo_off[f];
+        for (long long i0 = pl.c_first; i0 < pl.c_last; i0 += pl.K) {
+            const long long i1 = std::min(pl.c_last, i0 + pl.K), g0 = pl.C * i0, g1 = pl.seg_out_end(i0, i1);
+            if (g1 <= g0) continue;
+            amk::StreamView sv;
+            sv.fmt = (int)fmt; sv.total = pl.L; sv.lead = 0;
+            if (mem == AM_MEM_HOST) {
+                TRY(upload_segment(h, pl, streams[f], 0, seg_idx & 1, g0, std::min(pl.L, g1 + pl.m - 1), stage_threads, sv));
+            } else {
+                sv.x = streams[f]; sv.buf_first = 0; sv.buf_frames = (long long)frames[f];
+            }
+            TRY(compute_segment(h, pl, sv, i0, i1, pl.summary, false));
+            if (mem == AM_MEM_HOST) CU(cudaEventRecord(h->ev_done[seg_idx & 1], h->stream));
+            ++seg_idx;
+            if (h->progress) h->progress(h->progress_user, 0, (size_t)i0, (size_t)(i1 - i0));
+        }
+        acc.kernel_launches += h->stats.kernel_launches; acc.fft_blocks += h->stats.fft_blocks;
+        acc.h2d_bytes += h->stats.h2d_bytes; acc.frames += frames[f]; acc.chunks += (uint32_t)pl.num_chunks;
+        acc.fft_log2 = h->stats.fft_log2; acc.log2_n1 = h->stats.log2_n1; acc.log2_n2 = h->stats.log2_n2;
+        acc.summary_mode = std::max(acc.summary_mode, h->stats.summary_mode);
+    }
+
+    // one synchronisation, then the per-file host tails
+    std::vector<unsigned long long> cnt(2 * F, 0);
+    CU(cudaMemcpyAsync(cnt.data(), h->d_fcount.p, 2 * F * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    acc.d2h_bytes += 2 * F * sizeof(unsigned long long);
+    prof_collect(h);
+    size_t total = 0;
+    std::vector<am_peak> all, kept;
+    for (size_t f = 0; f < F; ++f) {
+        if (!queued[f]) { if (h->progress) h->progress(h->progress_user, 1, 0, 0); continue; }
+        const RangePlan &pl = pls[f];
+        const unsigned flags = (unsigned)cnt[2 * f + 1];
+        unsigned long long count = cnt[2 * f];
+        const amp::DevPeak *src = h->d_fpeaks.p + pk_off[f];
+        if ((flags & amp::FLAG_OVERFLOW) && count <= pk_cap[f])
+            return fail(AM_ERR_CAPACITY, "file %zu: a chunk kept more than max_peaks_per_chunk = %d peaks, or holds more than that many local "
+                                         "maxima of exactly equal height (raise it, the prominence or the distance)", f, pl.pk_cap);
+        if ((flags & (amp::FLAG_NEED_DENSE | amp::FLAG_OVERFLOW)) || count > pk_cap[f]) {
+            // rare: this file through the one-file path (summary pass + dense repeat of the marked chunks, full-size peak list)
+            const am_stats keep = h->stats;
+            TRY(range_pass_device(h, streams[f], 0, frames[f], frames[f], fmt, mem, scale, 0, (size_t)-1, &count));
+            acc.kernel_launches += h->stats.kernel_launches; acc.fft_blocks += h->stats.fft_blocks; acc.h2d_bytes += h->stats.h2d_bytes;
+            acc.d2h_bytes += h->stats.d2h_bytes; acc.dense_chunks += h->stats.dense_chunks;
+            acc.summary_mode = std::max(acc.summary_mode, h->stats.summary_mode);
+            h->stats = keep;
+            src = h->d_peaks.p;
+        } else if (h->progress) {
+            h->progress(h->progress_user, 1, 0, pl.num_chunks);
+        }
+        all.resize((size_t)count);
+        if (count) {
+            CU(cudaMemcpy(all.data(), src, (size_t)count * sizeof(am_peak), cudaMemcpyDeviceToHost));
+            acc.d2h_bytes += (size_t)count * sizeof(am_peak);
+        }
+        kept.resize(all.size());
+        size_t nk = 0;
+        TRY(am_merge_peaks(all.data(), all.size(), h->sr, h->cfg.distance_s, kept.data(), kept.size(), &nk));
+        n_out[f] = nk;
+        if (total + nk <= cap && nk) {
+            if (!out) return fail(AM_ERR_INVALID, "NULL output buffer");
+            memcpy(out + total, kept.data(), nk * sizeof(am_peak));
+        }
+        total += nk;
+    }
+    h->stats = acc;
+    if (total > cap) return fail(AM_ERR_CAPACITY, "%zu peaks, capacity %zu", total, cap);
     return AM_OK;
 }
 

@@ -273,6 +273,23 @@ class CudaConvolve:
                                              first_chunk, nc, int(final_filter), buf, cap, C.byref(got)))
         return buf, got.value
 
+    def _calc_files_raw(self, files, scale: bool, cap: int):
+        """-> (ctypes array of am_peak, per-file counts): one am_calc_chunks_files call over `files` (all in the same
+        sample format and memory space)."""
+        desc = [_describe(f) for f in files]
+        if not desc:
+            return (N.AmPeak * 1)(), []
+        fmt, mem = desc[0][2], desc[0][3]
+        if any(d[2] != fmt or d[3] != mem for d in desc):
+            raise TypeError("all files of one call must share the sample format and the memory space")
+        n = len(desc)
+        ptrs = (C.c_void_p * n)(*[d[0] for d in desc])
+        frames = (C.c_size_t * n)(*[d[1] for d in desc])
+        counts = (C.c_size_t * n)()
+        buf = (N.AmPeak * cap)()
+        N.check(N.lib().am_calc_chunks_files(self._h, n, ptrs, frames, fmt, mem, int(bool(scale)), buf, cap, counts))
+        return buf, list(counts)
+
 
 class StreamSession:
     """Push session (am_stream_begin / push / finish): calc_chunks for a decoder that yields the stream in pieces, the
@@ -341,6 +358,22 @@ def calc_chunks(sr: int, m_samples, algo_with_sample: CudaConvolve, scale: bool,
         raise ValueError(f"sample rate mismatch {algo_with_sample.sr} != {sr}")       # CliError::SampleRateMismatch
     algo_with_sample.set_config(config)
     return algo_with_sample._calc(m_samples, scale, None, 0, 0, None, True, cap)
+
+
+def calc_chunks_files(sr: int, files, algo_with_sample: CudaConvolve, scale: bool, config: Config,
+                      cap: int = 1 << 16) -> list[list[Peak]]:
+    """The loop over args.within of matcher::run (src/matcher/mod.rs:42-99: one calc_chunks per file against the same
+    snippet) as ONE library call: the work of all files is queued before the first result is read, so uploads
+    overlap matching across files.  -> one peak list per file, each equal to calc_chunks on that file."""
+    if int(sr) != algo_with_sample.sr:
+        raise ValueError(f"sample rate mismatch {algo_with_sample.sr} != {sr}")       # CliError::SampleRateMismatch
+    algo_with_sample.set_config(config)
+    buf, counts = algo_with_sample._calc_files_raw(list(files), scale, cap)
+    out, k = [], 0
+    for c in counts:
+        out.append([Peak._from_native(buf[k + i]) for i in range(c)])
+        k += c
+    return out
 
 
 def is_overshadowed(element: Peak, other: Peak | None, sr: int, max_distance: float) -> bool:

@@ -554,6 +554,36 @@ def _main(out_stream):
                                      "h2d_gbs": sst["h2d_bytes"] / dt / 1e9, "steps": 1, "timing": "wall clock",
                                      "offsets_equal": [(p.position.start, p.snippet_id) for p in s_peaks] == starts})
                 del arr
+            # many files, one snippet (the loop over args.within, src/matcher/mod.rs:42-99): the same PCM as one-hour files,
+            # one am_calc_chunks per file vs ONE am_calc_chunks_files call (uploads overlap matching across files)
+            per = sr * 3600
+            if ch == 1 and n_snip == 1 and host.shape[0] >= 2 * per:
+                files = [host[i * per:(i + 1) * per] for i in range(host.shape[0] // per)]
+                f_hours = len(files) * per / sr / 3600.0
+
+                def t_events(fn, reps):
+                    fn()
+                    torch.cuda.synchronize()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    for _ in range(reps):
+                        r = fn()
+                    b.record(stream)
+                    torch.cuda.synchronize()
+                    return a.elapsed_time(b) / reps, r
+
+                loop_ms, _ = t_events(lambda: [sh.algo._calc_raw(f, True, None, 0, 0, None, True, 1 << 10) for f in files], v_steps)
+                files_ms, (fbuf, fcounts) = t_events(lambda: sh.algo._calc_files_raw(files, True, 1 << 14), v_steps)
+                fst = sh.algo.stats()
+                found, k = [], 0
+                for i, c in enumerate(fcounts):
+                    found += [(i * per + fbuf[k + j].start, 0) for j in range(c)]
+                    k += c
+                variants.append({"host_memory": f"{len(files)} one-hour files, pinned int16, ONE am_calc_chunks_files call",
+                                 "value": f_hours / (files_ms / 1e3), "unit": UNIT, "ms_per_step": files_ms, "h2d_bytes_per_step": fst["h2d_bytes"],
+                                 "h2d_gbs": fst["h2d_bytes"] / (files_ms / 1e3) / 1e9, "steps": v_steps,
+                                 "one_call_per_file": {"value": f_hours / (loop_ms / 1e3), "unit": UNIT, "ms_per_step": loop_ms},
+                                 "peaks_found": len(found), "offsets_are_planted": len(found) > 0 and all(o in sh.expected for o in found)})
             e2e["variants"] = variants
         del host
 

@@ -61,6 +61,8 @@ extern "C" {
     fn am_out_len(n: usize, m: usize, mode: c_int) -> usize;
     fn am_correlate(h: *mut AmMatcher, within: *const c_void, n: usize, fmt: c_int, within_mem: c_int, mode: c_int,
                     scale: c_int, out: *mut f32, cap: usize, out_mem: c_int, out_len: *mut usize) -> c_int;
+    fn am_calc_chunks_files(h: *mut AmMatcher, n_files: usize, streams: *const *const c_void, frames: *const usize, fmt: c_int,
+                            mem: c_int, scale: c_int, out: *mut AmPeak, cap: usize, n_out: *mut usize) -> c_int;
     fn am_stream_begin(h: *mut AmMatcher, max_frames: usize, fmt: c_int, scale: c_int, out: *mut *mut AmStreamSession) -> c_int;
     fn am_stream_push(s: *mut AmStreamSession, pcm: *const c_void, frames: usize) -> c_int;
     fn am_stream_finish(s: *mut AmStreamSession, out: *mut AmPeak, cap: usize, n_out: *mut usize) -> c_int;
@@ -178,5 +180,52 @@ pub fn calc_chunks<Iter: ExactSizeIterator<Item = SampleType>>(
         right_diff: p.right_diff,
         height: Some(p.height),
         prominence: Some(p.prominence),
+    }).collect()
+}
+
+/// The loop `for main_file in &args.within` of `matcher::run` (src/matcher/mod.rs:42-99) as ONE library call, for callers
+/// that hold the decoded files (e.g. decoded on one thread per file): one peak list per file, each equal to
+/// `calc_chunks` on that file.  The work of all files is queued before the first result is read back, so the upload of
+/// file k+1 overlaps the matching of file k and short files keep the GPU busy.
+pub fn calc_chunks_files(
+    sr: u16,
+    files: &[Vec<SampleType>],
+    algo_with_sample: &CudaConvolve,
+    scale: bool,
+    config: Config,
+) -> Vec<Vec<find_peaks::Peak<SampleType>>> {
+    assert_eq!(sr, algo_with_sample.sr, "sample rate of the stream differs from the snippet's");
+    let cfg = AmConfig {
+        chunk_size_s: config.chunk_size.as_secs_f64(),
+        overlap_s: config.overlap_length.as_secs_f64(),
+        distance_s: config.peak_config.distance.as_secs_f64(),
+        prominence: config.peak_config.prominence,
+        fft_log2: 0,
+        max_peaks_per_chunk: 0,
+        reserved: 0,
+    };
+    let ptrs: Vec<*const c_void> = files.iter().map(|f| f.as_ptr().cast()).collect();
+    let frames: Vec<usize> = files.iter().map(Vec::len).collect();
+    let mut counts = vec![0usize; files.len()];
+    let mut peaks = vec![AmPeak::default(); 1 << 16];
+    unsafe {
+        assert_eq!(am_matcher_set_config(algo_with_sample.h, &cfg), 0, "{}", last_error());
+        assert_eq!(
+            am_calc_chunks_files(algo_with_sample.h, files.len(), ptrs.as_ptr(), frames.as_ptr(), AM_FMT_F32_MONO, AM_MEM_HOST,
+                                 c_int::from(scale), peaks.as_mut_ptr(), peaks.len(), counts.as_mut_ptr()),
+            0, "{}", last_error()
+        );
+    }
+    let mut rest = &peaks[..];
+    counts.iter().map(|&n| {
+        let (mine, tail) = rest.split_at(n);
+        rest = tail;
+        mine.iter().map(|p| find_peaks::Peak {
+            position: p.start as usize..p.end as usize,
+            left_diff: p.left_diff,
+            right_diff: p.right_diff,
+            height: Some(p.height),
+            prominence: Some(p.prominence),
+        }).collect()
     }).collect()
 }

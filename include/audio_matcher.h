@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define AM_ABI_VERSION 2
+#define AM_ABI_VERSION 3
 
 typedef enum {
     AM_OK = 0,
@@ -193,6 +193,15 @@ am_status am_calc_chunks_range(am_matcher *h, const void *stream, size_t buf_fir
  * over peaks gathered from all shards; host-only, `peaks` is reordered in place. */
 am_status am_merge_peaks(am_peak *peaks, size_t n, uint32_t sr, double distance_s, am_peak *out, size_t cap,
                          size_t *n_out);
+
+/* Several files per call: the loop over args.within of the reference (src/matcher/mod.rs:42-99, one calc_chunks per
+ * file against the same snippet).  streams[f] holds the frames[f] frames of file f (all files in `fmt` / `mem`).
+ * The work of all files is queued before the first result is read back, so the upload of file f+1 overlaps the
+ * kernels of file f and short files keep the GPU busy.  Peaks of file f are out[sum(n_out[0..f-1]) ...), n_out[f]
+ * of them, each list exactly what am_calc_chunks returns for that file; n_out has n_files entries and is filled
+ * even when the total exceeds cap (AM_ERR_CAPACITY). */
+am_status am_calc_chunks_files(am_matcher *h, size_t n_files, const void *const *streams, const size_t *frames,
+                               am_sample_fmt fmt, am_mem mem, int scale, am_peak *out, size_t cap, size_t *n_out);
 
 /* ---- push session: calc_chunks for a stream that arrives piece by piece --------------------------------------
  * The reference hands calc_chunks a lazy iterator of decoded frames with a claimed length (mp3_reader.rs:13-66,

@@ -155,6 +155,31 @@ inline std::vector<Peak> calc_chunks(uint32_t sr, const std::vector<float> &m_sa
     return out;
 }
 
+// The loop over args.within of matcher::run (src/matcher/mod.rs:42-99) as one library call: one peak list per file, each
+// equal to calc_chunks on that file; uploads overlap matching across files.
+inline std::vector<std::vector<Peak>> calc_chunks_files(uint32_t sr, const std::vector<std::vector<float>> &files,
+                                                        const CudaConvolve &algo, bool scale, const Config &config) {
+    if (sr != algo.sample_rate()) throw Error(AM_ERR_INVALID, "sample rate differs from the matcher's");
+    const am_config c = config.raw();
+    check(am_matcher_set_config(algo.handle(), &c));
+    std::vector<const void *> ptrs;
+    std::vector<std::size_t> frames, counts(files.size(), 0);
+    std::size_t cap = 64;
+    for (const auto &f : files) {
+        ptrs.push_back(f.data());
+        frames.push_back(f.size());
+        cap += am_num_chunks(algo.handle(), f.size()) * 64;
+    }
+    std::vector<am_peak> raw(cap);
+    check(am_calc_chunks_files(algo.handle(), files.size(), ptrs.data(), frames.data(), AM_FMT_F32_MONO, AM_MEM_HOST, scale ? 1 : 0,
+                               raw.data(), raw.size(), counts.data()));
+    std::vector<std::vector<Peak>> out(files.size());
+    std::size_t k = 0;
+    for (std::size_t f = 0; f < files.size(); ++f)
+        for (std::size_t i = 0; i < counts[f]; ++i) out[f].push_back(Peak::from(raw[k++]));
+    return out;
+}
+
 // is_overshadowed, audio_matcher.rs:143-160 (`other` may be absent)
 inline bool is_overshadowed(const Peak &element, const Peak *other, uint32_t sr, double max_distance_s) {
     if (!other) return false;

@@ -81,6 +81,25 @@ int main(void) {
         fprintf(stderr, "calc_chunks_sharded: %s\n", am_last_error());
         return 1;
     }
+    /* three "files" in one call (the loop over args.within, src/matcher/mod.rs:42): the KAT, an empty file, the KAT again */
+    {
+        const void *files[3] = {y, NULL, y};
+        size_t frames[3] = {7, 0, 7}, counts[3] = {9, 9, 9};
+        am_peak multi[8];
+        if (am_calc_chunks_files(g, 3, files, frames, AM_FMT_F32_MONO, AM_MEM_HOST, 1, multi, 8, counts) != AM_OK) {
+            fprintf(stderr, "calc_chunks_files: %s\n", am_last_error());
+            return 1;
+        }
+        if (counts[0] != 3 || counts[1] != 0 || counts[2] != 3 || multi[0].start != 1 || multi[2].start != 5 || multi[3].start != 1 ||
+            multi[4].prominence != streamed[1].prominence) {
+            fprintf(stderr, "calc_chunks_files differs from the one-file call (%zu %zu %zu)\n", counts[0], counts[1], counts[2]);
+            return 1;
+        }
+        if (am_calc_chunks_files(g, 3, files, frames, AM_FMT_F32_MONO, AM_MEM_HOST, 1, multi, 4, counts) != AM_ERR_CAPACITY || counts[2] != 3) {
+            fprintf(stderr, "calc_chunks_files: capacity overflow not reported\n");
+            return 1;
+        }
+    }
     am_matcher_destroy(g);
     am_matcher_destroy(h);
     printf("capi_smoke ok\n");

@@ -674,6 +674,83 @@ def test_host_memory_path_equals_device_path(am, orc, full_size):
     assert [(p.position.start, p.height, p.prominence) for p in c] == [(p.position.start, p.height, p.prominence) for p in a]
 
 
+def _peak_tuple(p):
+    return (p.position.start, p.position.stop, p.height, p.prominence, p.chunk)
+
+
+@pytest.mark.parametrize("mem", ["host", "device", "pinned"])
+def test_calc_chunks_files_equals_one_call_per_file(am, orc, mem):
+    """am_calc_chunks_files (the loop over args.within, src/matcher/mod.rs:42-99, as one call): every file's list must be
+    exactly what am_calc_chunks returns for that file -- files of different lengths (several segments down to less than
+    a chunk), one shorter than the snippet, an empty one, a loud coloured one that needs the dense repeat, and the
+    oracle on one of them."""
+    import torch
+    sr, m = 8000, 4000
+    rng = np.random.default_rng(77)
+    snip = orc.synth_pcm16(3001, 0, m)
+    lens = [sr * 33 + 17, sr * 4, m - 1, 0, sr * 61 + 5, sr * 12, sr * 20 + 3]
+    files = []
+    for i, n in enumerate(lens):
+        pcm = orc.synth_pcm16(4000 + i, 0, n)
+        for k, o in enumerate(range(5000 + 1000 * i, max(n - m, 0), 70001)):
+            orc.synth_plant(pcm, 1, snip, o, k % 3)
+        files.append(pcm)
+    files[5] = _coloured_noise(rng, lens[5], 0.97, 9000.0)                 # scores far below theta - prominence
+    for log2, chunk_s in ((0, 5.0), (20, 5.0), (15, 2.5)):
+        conf = am.Config(chunk_size=chunk_s, peak_config=am.PeakConfig(1.0, 0.11), fft_log2=log2)
+        algo = am.CudaConvolve(snip, sr=sr, config=conf)
+        if mem == "host":
+            arg = files
+        elif mem == "device":
+            arg = [torch.from_numpy(f).cuda() for f in files]
+        else:
+            arg = [torch.from_numpy(f).pin_memory() if f.size else torch.empty(0, dtype=torch.int16) for f in files]
+        single = [[_peak_tuple(p) for p in am.calc_chunks(sr, f, algo, True, conf)] for f in arg]
+        multi = am.calc_chunks_files(sr, arg, algo, True, conf)
+        st = algo.stats()
+        assert [[_peak_tuple(p) for p in l] for l in multi] == single
+        assert st["frames"] == sum(n for n in lens if n >= m) and st["kernel_launches"] > 0
+        assert len(single[0]) > 0 and len(single[4]) > 0 and single[2] == [] and single[3] == []
+        # a file that outgrows its share of the device peak list is repeated through the one-file path
+        os.environ["AM_FILES_MIN_CAP"] = "1"
+        try:
+            again = am.calc_chunks_files(sr, arg, algo, True, conf)
+        finally:
+            os.environ.pop("AM_FILES_MIN_CAP")
+        assert [[_peak_tuple(p) for p in l] for l in again] == single
+        # capacity: counts are still reported
+        buf_small = sum(len(x) for x in single) - 1
+        with pytest.raises(Exception):
+            am.calc_chunks_files(sr, arg, algo, True, conf, cap=buf_small)
+        # a second call on the same handle (buffers reused) and a plain call afterwards
+        assert [[_peak_tuple(p) for p in l] for l in am.calc_chunks_files(sr, arg[:2], algo, True, conf)] == single[:2]
+        assert [_peak_tuple(p) for p in am.calc_chunks(sr, arg[0], algo, True, conf)] == single[0]
+        algo.close()
+    x, s = orc.pcm16_to_f32(files[4]), orc.pcm16_to_f32(snip)
+    ref = orc.calc_chunks(x, s, sr, orc.make_config(2.5, m / sr, 1.0, 0.11), scale=True, precision=64, cap=1 << 18)
+    _assert_peaks(multi[4], [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
+
+
+def test_calc_chunks_files_at_full_block_length(am, orc, full_size):
+    """24 one-hour files (cfg 1-sized pieces of the 24 h stream, N = 2^22) in one call from pinned host memory == one
+    call per file, and the offsets found are planted ones."""
+    import torch
+    fs = full_size
+    sr, per = fs["sr"], fs["sr"] * 3600
+    host = torch.empty(6 * per, dtype=torch.int16, pin_memory=True)
+    host.copy_(fs["pcm"][:6 * per])
+    torch.cuda.synchronize()
+    files = [host[i * per:(i + 1) * per] for i in range(6)]
+    multi = am.calc_chunks_files(sr, files, fs["algo"], True, fs["conf"])
+    st = fs["algo"].stats()
+    single = [am.calc_chunks(sr, f, fs["algo"], True, fs["conf"]) for f in files]
+    assert [[_peak_tuple(p) for p in l] for l in multi] == [[_peak_tuple(p) for p in l] for l in single]
+    found = [i * per + p.position.start for i, l in enumerate(multi) for p in l]
+    assert len(found) >= 20 and all(o in fs["planted"] for o in found)
+    # (a one-hour file is two upload segments; the second re-sends the overlap of the segment boundary)
+    assert 6 * per * 2 <= st["h2d_bytes"] <= 6 * (per + 2 * fs["m"]) * 2 and st["chunks"] == 6 * 60
+
+
 @pytest.mark.parametrize("env", [{"AM_COL_STREAM": "0"}, {"AM_ROW_STREAM": "1"}, {"AM_ROW_STREAM": "0"}, {"AM_BATCH_SNIPPETS": "3"}])
 def test_alternate_kernel_paths(env):
     """The kernel choices are read once per process; the non-default ones (plain-grid forward column kernel that also

@@ -1,7 +1,7 @@
 """Randomised parity soak (run by hand on a GPU box: python tests/fuzz_gpu.py [seconds] [seed]).
 Random stream / snippet material (white, coloured, tonal, loud, quiet), chunk geometry (incl. ov != m), block length,
 minimum distance, prominence and candidate cap; calc_chunks through the C ABI (one-shot, push session, 3-way shard +
-merge) must equal the CPU oracle: offsets bit-exact, heights / prominences within 1e-4 relative."""
+merge, several files per call) must equal the CPU oracle: offsets bit-exact, heights / prominences within 1e-4 relative."""
 import os
 import sys
 import time
@@ -111,6 +111,13 @@ def one_case(rng, case):
             if b > a:
                 parts += algo._calc(np.ascontiguousarray(pcm[lo:hi]), True, n, lo, a, b - a, False, 1 << 20)
         same(am.merge_peaks(parts, sr, dist), "shards + merge")
+        # several files in one call (am_calc_chunks_files): the stream, its first half, the stream again
+        half = np.ascontiguousarray(pcm[:n // 2])
+        multi = am.calc_chunks_files(sr, [pcm, half, pcm], algo, True, conf, cap=1 << 20)
+        same(multi[0], "files[0]")
+        same(multi[2], "files[2]")
+        key = lambda l: [(p.position.start, p.position.stop, p.height, p.prominence, p.chunk) for p in l]
+        assert key(multi[1]) == key(am.calc_chunks(sr, half, algo, True, conf, cap=1 << 20)), ("files[1]", desc)
     except Borderline:
         return "threshold-borderline"
     except N.NativeError as e:

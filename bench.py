@@ -392,6 +392,47 @@ def measure_config(name, wl, world, rank, stream, steps, warmup, distance_s=DIST
     return rec
 
 
+def measure_files(name, wl, stream, n_files, steps, warmup):
+    """The reference's run over many files (`for main_file in &args.within`, src/matcher/mod.rs:42-99) on its own
+    CPU-runnable config: `n_files` files of the workload's length, resident in HBM, matched with ONE
+    am_calc_chunks_files call vs one am_calc_chunks call per file."""
+    import torch
+    sr, ch, snip_s, hours, fft_log2, n_snip = wl
+    sh = Shard(name, wl, 1, 0, stream, total_hours=hours * n_files)
+    per = int(round(hours * 3600 * sr))
+    files = [sh.pcm[i * per:(i + 1) * per] for i in range(n_files)]
+
+    def t_events(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            r = fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps, r
+
+    loop_ms, _ = t_events(lambda: [sh.algo._calc_raw(f, True, None, 0, 0, None, True, 1 << 10) for f in files])
+    files_ms, (buf, counts) = t_events(lambda: sh.algo._calc_files_raw(files, True, 1 << 14))
+    stats = sh.algo.stats()
+    found, k = [], 0
+    for i, c in enumerate(counts):
+        found += [(i * per + buf[k + j].start, 0) for j in range(c)]
+        k += c
+    total_h = n_files * hours
+    rec = {"workload": f"{name} x {n_files} files: {workload_name(name, wl)}; one am_calc_chunks_files call over all files",
+           "n_gpus": 1, "hours_total": total_h, "value": total_h / (files_ms / 1e3), "unit": UNIT, "ms_per_step": files_ms, "steps": steps,
+           "one_call_per_file": {"value": total_h / (loop_ms / 1e3), "unit": UNIT, "ms_per_step": loop_ms},
+           "fft_log2": stats["fft_log2"], "four_step": f"{1 << stats['log2_n1']}x{1 << stats['log2_n2']}",
+           "summary_mode": stats["summary_mode"], "dense_chunks": stats.get("dense_chunks", 0), "n_snippets": 1,
+           "peaks_found": len(found), "planted": len(sh.plan),
+           "verified_offsets_are_planted": len(found) > 0 and all(o in sh.expected for o in found), "kernel_ms_per_step": {}}
+    sh.close()
+    return rec
+
+
 def main():
     # keep stdout clean for the single JSON line: libraries (NCCL's version banner, torchrun notices)
     # write to fd 1 too, so everything else goes to stderr
@@ -604,6 +645,7 @@ def _main(out_stream):
             add(lambda: measure_config("cfg1", WORKLOADS["cfg1"], 1, 0, stream, 10, 3, verify_chunks=0 if args.no_verify else 2))
             for d in (8.0, 20.0, 60.0, 120.0):                      # benches/my_benchmark.rs:95, --distance sweep on cfg 1
                 add(lambda d=d: measure_config("cfg1", WORKLOADS["cfg1"], 1, 0, stream, 10, 3, distance_s=d))
+            add(lambda: measure_files("cfg1", WORKLOADS["cfg1"], stream, 24, 5, 2))
             # summary-mode robustness: the headline workload on loud coloured programme material (ratio to the white-noise step)
             def loud():
                 r = measure_config("cfg2", WORKLOADS["cfg2"], 1, 0, stream, 5, 2, verify_chunks=0 if args.no_verify else 2, coloured=True)

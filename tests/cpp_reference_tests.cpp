@@ -33,6 +33,12 @@ static Three test_peaks(bool gpu) {
     auto peaks = calc_chunks(1, {0.f, 0.7f, 0.5f, 1.0f, 0.5f, 0.8f, 0.f}, one_tap, true, conf);
     ASSERT(peaks.size() == 3);
     if (peaks.size() != 3) return {peak(3, 1.0f), peak(5, 0.3f), peak(1, 0.2f)};
+    // the same stream as two "files" of one run (the loop over args.within, src/matcher/mod.rs:42) plus an empty one
+    const std::vector<float> y = {0.f, 0.7f, 0.5f, 1.0f, 0.5f, 0.8f, 0.f};
+    const auto per_file = calc_chunks_files(1, {y, {}, y}, one_tap, true, conf);
+    ASSERT(per_file.size() == 3 && per_file[0].size() == 3 && per_file[1].empty() && per_file[2].size() == 3);
+    if (per_file.size() == 3 && per_file[2].size() == 3)
+        for (int i = 0; i < 3; ++i) ASSERT(per_file[2][i].start == peaks[i].start && *per_file[2][i].prominence == *peaks[i].prominence);
     // calc_chunks sorts by start: 1, 3, 5
     const Peak p3 = peaks[0], p1 = peaks[1], p2 = peaks[2];
     ASSERT(p3.start == 1 && std::fabs(*p3.prominence - 0.2f) < 1e-6f);

@@ -20,6 +20,7 @@
 #include <thread>
 #include <vector>
 
+#include <chrono>
 #include <condition_variable>
 
 #include <cuda.h>
@@ -188,13 +189,22 @@ struct HostStager {
         return cudaSuccess;
     }
     cudaError_t upload(void *dst_dev, const void *src, size_t bytes, cudaStream_t s) {
-        for (size_t o = 0; o < bytes; o += CHUNK, slot = (slot + 1) % SLOTS) {
-            const size_t n = std::min(CHUNK, bytes - o);
+        static const bool dbg = getenv("AM_STAGE_DEBUG") != nullptr;
+        static const size_t piece = [] { const char *v = getenv("AM_STAGE_CHUNK_MB"); size_t mb = v && *v ? (size_t)atoi(v) : 8; return std::min<size_t>(std::max<size_t>(mb, 1), 32) << 20; }();
+        double t_acq = 0, t_copy = 0, t_send = 0;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        for (size_t o = 0; o < bytes; o += piece, slot = (slot + 1) % SLOTS) {
+            const size_t n = std::min(piece, bytes - o);
             cudaError_t e;
+            const double t0 = dbg ? now() : 0;
             if ((e = acquire(slot)) != cudaSuccess) return e;
+            const double t1 = dbg ? now() : 0;
             parallel_copy(pinned[slot], (const char *)src + o, n);
+            const double t2 = dbg ? now() : 0;
             if ((e = send(slot, (char *)dst_dev + o, n, s)) != cudaSuccess) return e;
+            if (dbg) { const double t3 = now(); t_acq += t1 - t0; t_copy += t2 - t1; t_send += t3 - t2; }
         }
+        if (dbg) fprintf(stderr, "[stager] %zu MB: acquire %.2f ms, copy %.2f ms (%.1f GB/s), send %.2f ms\n", bytes >> 20, t_acq, t_copy, bytes / t_copy / 1e6, t_send);
         return cudaSuccess;
     }
     void release() {
@@ -1224,7 +1234,7 @@ static am_status upload_segment(am_matcher *h, const RangePlan &pl, const void *
     CU(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // kernels that read this buffer are done
     TRY(h->d_stage[b].reserve(bytes));
     const unsigned char *src = (const unsigned char *)stream + (size_t)(f_lo - (long long)buf_first_frame) * pl.fb;
-    if (stage_threads > 0 && bytes >= ((size_t)64 << 20) && h->stager.ensure(stage_threads))
+    if (stage_threads > 0 && bytes >= ((size_t)1 << 20) && h->stager.ensure(stage_threads))
         CU(h->stager.upload(h->d_stage[b].p, src, bytes, h->copy_stream));
     else
         CU(cudaMemcpyAsync(h->d_stage[b].p, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));

@@ -731,6 +731,27 @@ def test_calc_chunks_files_equals_one_call_per_file(am, orc, mem):
     _assert_peaks(multi[4], [[p.start, p.end, p.height, p.prominence, p.chunk] for p in ref])
 
 
+def test_calc_chunks_files_with_a_batch_of_snippets(am, orc):
+    """Several files x several snippets (am_matcher_create_batch): per file the snippet-major list of the one-file call."""
+    sr, m = 8000, 3000
+    snips = [orc.synth_pcm16(500 + i, 0, m) for i in range(3)]
+    files = []
+    for f, n in enumerate([sr * 41, sr * 7 + 3, sr * 23]):
+        pcm = orc.synth_pcm16(80 + f, 0, n)
+        for k, o in enumerate(range(9000, n - m, 45001)):
+            orc.synth_plant(pcm, 1, snips[(k + f) % 3], o, k % 2)
+        files.append(pcm)
+    for log2 in (14, 20):
+        conf = am.Config(chunk_size=5.0, peak_config=am.PeakConfig(2.0, 0.13), fft_log2=log2)
+        batch = am.CudaConvolve(np.stack([orc.pcm16_to_f32(s) for s in snips]), sr=sr, config=conf, batch=True)
+        key = lambda l: [(p.snippet_id,) + _peak_tuple(p) for p in l]
+        single = [key(am.calc_chunks(sr, f, batch, True, conf)) for f in files]
+        multi = am.calc_chunks_files(sr, files, batch, True, conf)
+        assert [key(l) for l in multi] == single and sum(len(l) for l in single) >= 6
+        assert all([p.snippet_id for p in l] == sorted(p.snippet_id for p in l) for l in multi)
+        batch.close()
+
+
 def test_calc_chunks_files_at_full_block_length(am, orc, full_size):
     """24 one-hour files (cfg 1-sized pieces of the 24 h stream, N = 2^22) in one call from pinned host memory == one
     call per file, and the offsets found are planted ones."""

@@ -85,6 +85,16 @@ def one_case(rng, case):
             if shifted and len(shifted) == len(only_a) == len(only_b):
                 counts_ties[0] += len(shifted)
                 raise Borderline()
+            # ... and twins: two local maxima of one chunk whose heights agree to fp32 rounding.  The walk of the (by a
+            # rounding) lower one stops at the other, so it keeps only the dip between them as prominence and falls
+            # under the threshold; which of the two survives may differ between an f64 and an f32 correlation.
+            ha = {k: p.height for k, p in zip(a, got)}
+            hb = {k: p.height for k, p in zip(b, ref)}
+            twins = {k for k in only_a for q in only_b if k[2] == q[2] and abs(ha[k] - hb[q]) <= 2e-6 * max(1.0, abs(hb[q]))
+                     and abs(pa[k] - pb[q]) <= 1e-5 * max(1.0, abs(pb[q]))}
+            if twins and len(twins) == len(only_a) == len(only_b):
+                counts_ties[0] += len(twins)
+                raise Borderline()
             odd = [pa.get(k, pb.get(k)) for k in set(a) ^ set(b)]
             assert odd and (dist > 0 or all(abs(q - prom) <= 1e-4 * prom for q in odd)), (what, desc, sorted(set(a) ^ set(b))[:6], odd[:6], len(a), len(b))
             assert any(abs(q - prom) <= 1e-4 * prom for q in list(pa.values()) + list(pb.values())), (what, desc, len(a), len(b))

@@ -1423,12 +1423,16 @@ am_status am_calc_chunks_files(am_matcher *h, size_t n_files, const void *const 
     TRY(h->d_fredo.reserve(std::max<size_t>(redo_off[F], 1)));
     CU(cudaMemsetAsync(h->d_fcount.p, 0, 2 * F * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_fredo.p, 0, std::max<size_t>(redo_off[F], 1), h->stream));
-    int stage_threads = 0;
-    if (mem == AM_MEM_HOST && streams[fmax]) {
-        cudaPointerAttributes pa;
-        if (cudaPointerGetAttributes(&pa, streams[fmax]) == cudaSuccess && pa.type == cudaMemoryTypeUnregistered) stage_threads = HostStager::default_threads();
-        cudaGetLastError();
-    }
+    // pageable files go through the pinned ring, pinned / registered ones straight to the copy engine (per file)
+    auto stage_threads_of = [&](const void *p) {
+        int t = 0;
+        if (mem == AM_MEM_HOST && p) {
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, p) == cudaSuccess && pa.type == cudaMemoryTypeUnregistered) t = HostStager::default_threads();
+            cudaGetLastError();
+        }
+        return t;
+    };
 
     // queue every file
     am_stats acc;
@@ -1441,6 +1445,7 @@ am_status am_calc_chunks_files(am_matcher *h, size_t n_files, const void *const 
         TRY(plan_range(h, frames[f], fmt, mem == AM_MEM_HOST, scale, 0, (size_t)-1, pl, &nothing));
         if (nothing) continue;
         queued[f] = 1;
+        const int stage_threads = stage_threads_of(streams[f]);
         pl.po.peaks = h->d_fpeaks.p + pk_off[f]; pl.po.cap = pk_cap[f]; pl.dev_cap = pk_cap[f];
         pl.po.count = h->d_fcount.p + 2 * f; pl.po.flags = (unsigned *)(h->d_fcount.p + 2 * f + 1);
         pl.po.redo = h->d_fredo.p + redo_off[f];

@@ -678,7 +678,7 @@ def _peak_tuple(p):
     return (p.position.start, p.position.stop, p.height, p.prominence, p.chunk)
 
 
-@pytest.mark.parametrize("mem", ["host", "device", "pinned"])
+@pytest.mark.parametrize("mem", ["host", "device", "pinned", "mixed"])
 def test_calc_chunks_files_equals_one_call_per_file(am, orc, mem):
     """am_calc_chunks_files (the loop over args.within, src/matcher/mod.rs:42-99, as one call): every file's list must be
     exactly what am_calc_chunks returns for that file -- files of different lengths (several segments down to less than
@@ -703,6 +703,8 @@ def test_calc_chunks_files_equals_one_call_per_file(am, orc, mem):
             arg = files
         elif mem == "device":
             arg = [torch.from_numpy(f).cuda() for f in files]
+        elif mem == "mixed":                                                # pageable and pinned files in one call
+            arg = [torch.from_numpy(f).pin_memory() if (i % 2 and f.size) else f for i, f in enumerate(files)]
         else:
             arg = [torch.from_numpy(f).pin_memory() if f.size else torch.empty(0, dtype=torch.int16) for f in files]
         single = [[_peak_tuple(p) for p in am.calc_chunks(sr, f, algo, True, conf)] for f in arg]

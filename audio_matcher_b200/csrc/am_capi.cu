@@ -601,19 +601,24 @@ am_status ensure_workspace(am_matcher *h, int log2n, unsigned long long pairs_to
     // launch groups of 256 block pairs at N = 2^22 (8 GB): larger groups amortise the launch tails and gaps (64 pairs
     // 22.8, 128 pairs 22.5, 256 pairs 22.2 ms per 24 h); a batch keeps 2 GB groups, its second workspace holds
     // several snippets per group
+    // The defaults assume a B200 to ourselves; when the device cannot give that much (other tenants, other
+    // matchers) the group is halved until it fits -- smaller launch groups cost a few percent, not the call.
     size_t budget = env_mb("AM_WORKSPACE_MB", h->S > 1 ? 2048 : 8192) << 20;
-    size_t per_pair = sizeof(float2) << log2n;
-    unsigned long long g = std::max<size_t>(1, budget / per_pair);
-    g = std::min<unsigned long long>(g, pairs_total);
-    g = std::min<unsigned long long>(g, 32768);
-    TRY(h->d_A.reserve((size_t)g << log2n));
-    if (h->S > 1) {
-        int l1, l2;
-        split(log2n, l1, l2);
-        TRY(h->d_B.reserve(((size_t)g << log2n) * (size_t)batch_snippets_per_launch(l2, h->S)));
+    const size_t per_pair = sizeof(float2) << log2n;
+    int l1, l2;
+    split(log2n, l1, l2);
+    for (;;) {
+        unsigned long long g = std::max<size_t>(1, budget / per_pair);
+        g = std::min<unsigned long long>(g, pairs_total);
+        g = std::min<unsigned long long>(g, 32768);
+        am_status st = h->d_A.reserve((size_t)g << log2n);
+        if (st == AM_OK && h->S > 1) st = h->d_B.reserve(((size_t)g << log2n) * (size_t)batch_snippets_per_launch(l2, h->S));
+        if (st == AM_OK) { pairs_per_group = g; return AM_OK; }
+        if (st != AM_ERR_NOMEM || g <= 1) return st;
+        cudaGetLastError();
+        h->d_A.release(); h->d_B.release();
+        budget = std::max(per_pair, (size_t)(g / 2) * per_pair);
     }
-    pairs_per_group = g;
-    return AM_OK;
 }
 
 // conjugate spectrum of the zero-padded snippet for block length 2^log2n, computed once per
@@ -1170,15 +1175,24 @@ static am_status plan_range(am_matcher *h, size_t total_frames, am_sample_fmt fm
     }
     size_t seg_floats = (env_mb("AM_SEGMENT_MB", seg_mb) << 20) / sizeof(float) / S;
     if (S > 1) seg_floats = std::max<size_t>(seg_floats, (size_t)48 << 20);
-    pl.K = std::max<long long>(1, (long long)(seg_floats / (size_t)C));
-    pl.K = std::min<long long>(pl.K, (long long)num_chunks);
-    pl.seg_c_len = ((pl.K * C + std::max<long long>(ov - m + 1, 0) + 1 + 15) / 16) * 16;   // float4 / run alignment per snippet
-    TRY(h->d_c.reserve((size_t)pl.seg_c_len * S));
-    if (pl.summary) TRY(h->d_rsum.reserve(((size_t)pl.seg_c_len * S) >> 4));
-    pl.recs = amp::RunRecs{h->d_rsum.p};
     pl.tiles_stride = ((C + std::max<long long>(ov - m + 1, 1)) + amp::TP - 1) / amp::TP + 1;
-    TRY(h->d_tmin.reserve((size_t)(pl.K * pl.tiles_stride) * S));
-    TRY(h->d_tmax.reserve((size_t)(pl.K * pl.tiles_stride) * S));
+    for (;;) {
+        // the segment buffers are sized for a B200 to ourselves; when the device cannot give that much the segment is
+        // halved (down to one logical chunk) until they fit
+        pl.K = std::max<long long>(1, (long long)(seg_floats / (size_t)C));
+        pl.K = std::min<long long>(pl.K, (long long)num_chunks);
+        pl.seg_c_len = ((pl.K * C + std::max<long long>(ov - m + 1, 0) + 1 + 15) / 16) * 16;   // float4 / run alignment per snippet
+        am_status st = h->d_c.reserve((size_t)pl.seg_c_len * S);
+        if (st == AM_OK && pl.summary) st = h->d_rsum.reserve(((size_t)pl.seg_c_len * S) >> 4);
+        if (st == AM_OK) st = h->d_tmin.reserve((size_t)(pl.K * pl.tiles_stride) * S);
+        if (st == AM_OK) st = h->d_tmax.reserve((size_t)(pl.K * pl.tiles_stride) * S);
+        if (st == AM_OK) break;
+        if (st != AM_ERR_NOMEM || pl.K <= 1) return st;
+        cudaGetLastError();
+        h->d_c.release(); h->d_rsum.release(); h->d_tmin.release(); h->d_tmax.release();
+        seg_floats = (size_t)(pl.K / 2) * (size_t)C;
+    }
+    pl.recs = amp::RunRecs{h->d_rsum.p};
     pl.pk_cap = h->cfg.max_peaks_per_chunk ? (int)h->cfg.max_peaks_per_chunk : 1024;
     if (amp::chunk_peaks_smem(pl.pk_cap, 0) > 200 * 1024) return fail(AM_ERR_INVALID, "max_peaks_per_chunk %d too large", pl.pk_cap);
     pl.sm_tiles = 0;                                         // tile summaries staged in shared memory when they fit

@@ -674,6 +674,32 @@ def test_host_memory_path_equals_device_path(am, orc, full_size):
     assert [(p.position.start, p.height, p.prominence) for p in c] == [(p.position.start, p.height, p.prominence) for p in a]
 
 
+def test_device_memory_pressure_shrinks_the_buffers(am, orc, full_size):
+    """The workspace (8 GiB) and segment (16 GiB) defaults assume a B200 to ourselves.  With ~3 GiB left on the device a
+    new matcher must still run -- smaller launch groups and segments -- and find the same offsets."""
+    import torch
+    fs = full_size
+    sr, frames = fs["sr"], fs["sr"] * 3600 * 6
+    ref = am.calc_chunks(sr, fs["pcm"][:frames], fs["algo"], True, fs["conf"])
+    launches_unconstrained = fs["algo"].stats()["kernel_launches"]
+    algo2 = am.CudaConvolve(fs["snip"], sr=sr, config=fs["conf"])
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    filler = torch.empty(max(free - (3 << 30), 1), dtype=torch.uint8, device="cuda")
+    try:
+        got = am.calc_chunks(sr, fs["pcm"][:frames], algo2, True, fs["conf"])
+        st = algo2.stats()
+    finally:
+        del filler
+        torch.cuda.empty_cache()
+        algo2.close()
+    assert len(ref) > 10 and [p.position.start for p in got] == [p.position.start for p in ref]
+    for a, b in zip(got, ref):                                             # (other segment / block tiling: rounding only)
+        assert abs(a.height - b.height) <= 1e-5 * abs(b.height) and abs(a.prominence - b.prominence) <= 1e-5 * abs(b.prominence)
+    assert st["summary_mode"] == 1 and st["chunks"] == 360
+    assert st["kernel_launches"] > launches_unconstrained                  # more, smaller launch groups / segments
+
+
 def _peak_tuple(p):
     return (p.position.start, p.position.stop, p.height, p.prominence, p.chunk)
 

@@ -3,6 +3,7 @@
 
   correlate_vs_bib      (:29-53)  snippet 100..150 vs stream -2000..2000, Mode::Valid, unscaled
   correlate_vs_conj     (:55-79)  same shapes; here: direct-sum kernel vs block-FFT kernel
+  correlate_chunk       (audio_matcher.rs:120-122) correlate_with_sample on one logical chunk window, host buffers
   compare_chunk_sizes   (:81-108) full calc_chunks with --distance 8/20/60/120 s on the 1 h 44.1 kHz workload
                                   (the reference's res/local/*.mp3 are not shipped; BASELINE.json configs[0] shapes)
 
@@ -61,6 +62,20 @@ def main():
         emit("compare_chunk_sizes", f"peaks in 1 h synthetic stream/{distance} (host PCM, H2D included)",
              lambda: am.calc_chunks(sr, pcm, algo, True, conf), min_time=1.0, max_iters=200)
         algo.close()
+
+    # the fine seam alone (CorrelateAlgo::correlate_with_sample, audio_matcher.rs:67-72, what calc_chunks calls once per
+    # logical chunk, :120-122): one 60 s + overlap window of f32 samples in host memory in, the scaled Valid correlation in
+    # host memory out -- what a maintainer gets by swapping only LibConvolve::new for CudaConvolve::new
+    window = orc.pcm16_to_f32(pcm[:60 * sr + len(snip)])
+    algo = am.CudaConvolve(snip, sr=sr, config=am.Config(fft_log2=22))
+    emit("correlate_chunk", f"correlate_with_sample, one {len(window)}-sample window vs {len(snip)}-sample snippet (host f32 in / out)",
+         lambda: algo.correlate_with_sample(window, am.Mode.Valid, True), min_time=1.0, max_iters=200)
+    import time as _t
+    t0 = _t.perf_counter()
+    orc.correlate(window, orc.pcm16_to_f32(snip), orc.MODE_VALID, 32)
+    print(json.dumps({"group": "correlate_chunk", "name": "the same window through the CPU oracle port (f32 exact-length FFT, 1 thread)",
+                      "mean_us": round(1e6 * (_t.perf_counter() - t0), 2), "iters": 1}), flush=True)
+    algo.close()
 
 
 if __name__ == "__main__":

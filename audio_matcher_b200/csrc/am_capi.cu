@@ -9,6 +9,7 @@
 //   * calc_chunks' tail: stable sort by start + filter_surrounding/is_overshadowed
 //     (src/matcher/audio_matcher.rs:132-160) over the handful of surviving peaks
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -94,7 +95,7 @@ template <class T> struct DevBuf {
 }  // namespace
 
 // Upload of PAGEABLE host memory (what a Vec / numpy caller or a decoder thread hands over).  cudaMemcpyAsync stages
-// such memory inside the driver at ~11 GB/s; here a persistent pool of host threads copies 32 MB chunks into a small
+// such memory inside the driver at ~11 GB/s; here a persistent pool of host threads copies 8 MB chunks into a small
 // ring of pinned buffers and each chunk goes out with ONE asynchronous copy while the next one is being filled.
 // Pinned / registered memory handed to the one-shot entry points never comes here.
 struct HostStager {
@@ -112,8 +113,15 @@ struct HostStager {
     const char *job_src = nullptr;
     size_t job_n = 0, job_piece = 0, job_pieces = 0, next_piece = 0, pieces_done = 0;
     unsigned long long generation = 0;
+    std::atomic<unsigned long long> generation_pub{0};   // copy of `generation` the workers may poll without the lock
     bool stop = false;
 
+    // bytes per slot fill / asynchronous copy: 8 MB fills run at ~71 GB/s, 32 MB fills at ~45 (the ring then no longer
+    // stays cache-resident); AM_STAGE_CHUNK_MB overrides (1..32)
+    static size_t fill_bytes() {
+        static const size_t piece = [] { const char *v = getenv("AM_STAGE_CHUNK_MB"); size_t mb = v && *v ? (size_t)atoi(v) : 8; return std::min<size_t>(std::max<size_t>(mb, 1), 32) << 20; }();
+        return piece;
+    }
     static int default_threads() {
         static const int env = [] { const char *v = getenv("AM_STAGE_THREADS"); return v && *v ? atoi(v) : -1; }();
         if (env >= 0) return env;
@@ -141,6 +149,19 @@ struct HostStager {
         std::unique_lock<std::mutex> lk(mu);
         unsigned long long seen = 0;
         for (;;) {
+            if (!stop && generation == seen) {
+                // a decoder pushes block after block: poll for the next job for a moment before going to sleep
+                // (a condition-variable wake-up costs about as much as copying a 4 MB push)
+                lk.unlock();
+                const auto t0 = std::chrono::steady_clock::now();
+                while (generation_pub.load(std::memory_order_acquire) == seen &&
+                       std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(150)) {
+#if defined(__x86_64__) || defined(__i386__)
+                    __builtin_ia32_pause();
+#endif
+                }
+                lk.lock();
+            }
             cv_work.wait(lk, [&] { return stop || (generation != seen && next_piece < job_pieces); });
             if (stop) return;
             seen = generation;
@@ -162,6 +183,7 @@ struct HostStager {
         job_pieces = (n + job_piece - 1) / job_piece;
         next_piece = 0; pieces_done = 0;
         ++generation;
+        generation_pub.store(generation, std::memory_order_release);
         cv_work.notify_all();
         size_t i;
         while (take_piece(i)) {
@@ -190,7 +212,7 @@ struct HostStager {
     }
     cudaError_t upload(void *dst_dev, const void *src, size_t bytes, cudaStream_t s) {
         static const bool dbg = getenv("AM_STAGE_DEBUG") != nullptr;
-        static const size_t piece = [] { const char *v = getenv("AM_STAGE_CHUNK_MB"); size_t mb = v && *v ? (size_t)atoi(v) : 8; return std::min<size_t>(std::max<size_t>(mb, 1), 32) << 20; }();
+        const size_t piece = fill_bytes();
         double t_acq = 0, t_copy = 0, t_send = 0;
         auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         for (size_t o = 0; o < bytes; o += piece, slot = (slot + 1) % SLOTS) {
@@ -1537,7 +1559,7 @@ am_status am_calc_chunks_files(am_matcher *h, size_t n_files, const void *const 
 // ---- push session: calc_chunks for a decoder that produces the stream piece by piece -------------------
 // The reference feeds calc_chunks a lazy iterator of decoded frames (mp3_reader.rs:13-66, matcher/mod.rs:71-83).
 // Here the decoder thread pushes whatever it has; frames collect in the pinned ring (one asynchronous copy per
-// 32 MB, or per segment end) and land in one of two device segment buffers.  As soon as the frames of a segment of
+// 8 MB, or per segment end) and land in one of two device segment buffers.  As soon as the frames of a segment of
 // K logical chunks are complete its transforms + peak kernels are launched, so matching overlaps decoding and the
 // uploads; only the last, partial segment is left for am_stream_finish.
 struct am_stream_session {
@@ -1668,7 +1690,7 @@ am_status am_stream_push(am_stream_session *s, const void *pcm, size_t frames) {
                 s->slot_fill = 0;
                 s->slot_first = s->pushed;
             }
-            const long long slot_room = (long long)((HostStager::CHUNK - s->slot_fill) / fb);
+            const long long slot_room = (long long)((HostStager::fill_bytes() - s->slot_fill) / fb);
             const long long take = std::min(left, std::min(room, slot_room));
             h->stager.parallel_copy((char *)h->stager.pinned[s->slot] + s->slot_fill, src, (size_t)take * fb);
             s->slot_fill += (size_t)take * fb;

@@ -580,17 +580,17 @@ def _main(out_stream):
                                  "offsets_equal": [(p.position.start, p.snippet_id) for p in v_peaks] == starts})
                 if arr.dtype == np.float32:
                     # exactly what ffi/cuda_convolve.rs does with the reference's sample iterator: a push session fed with
-                    # 1 Mi-sample f32 blocks (am_stream_begin / am_stream_push / am_stream_finish), wall clock
+                    # 4 Mi-sample f32 blocks (am_stream_begin / am_stream_push / am_stream_finish), wall clock
                     from audio_matcher_b200.matcher import StreamSession
                     from audio_matcher_b200 import _native as N
                     t0 = time.perf_counter()
                     st = StreamSession(sh.algo, len(arr), N.FMT_F32_MONO, True, 1 << 14)
-                    for i in range(0, len(arr), 1 << 20):
-                        st.push(arr[i:i + (1 << 20)])
+                    for i in range(0, len(arr), 1 << 22):
+                        st.push(arr[i:i + (1 << 22)])
                     s_peaks = st.finish()
                     dt = time.perf_counter() - t0
                     sst = sh.algo.stats()
-                    variants.append({"host_memory": "push session, pageable f32 blocks of 2^20 samples (the Rust shim's calc_chunks)",
+                    variants.append({"host_memory": "push session, pageable f32 blocks of 2^22 samples (the Rust shim's calc_chunks)",
                                      "value": sh.hours_total() / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "h2d_bytes_per_step": sst["h2d_bytes"],
                                      "h2d_gbs": sst["h2d_bytes"] / dt / 1e9, "steps": 1, "timing": "wall clock",
                                      "offsets_equal": [(p.position.start, p.snippet_id) for p in s_peaks] == starts})

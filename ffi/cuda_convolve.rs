@@ -148,7 +148,7 @@ pub fn calc_chunks<Iter: ExactSizeIterator<Item = SampleType>>(
         max_peaks_per_chunk: 0,
         reserved: 0,
     };
-    const BLOCK: usize = 1 << 20;
+    const BLOCK: usize = 1 << 22; // 16 MB of f32 per push: the library copies it into its pinned ring with a pool of threads
     let mut block: Vec<SampleType> = Vec::with_capacity(BLOCK);
     let mut peaks = vec![AmPeak::default(); 1 << 16];
     let mut n = 0usize;

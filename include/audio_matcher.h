@@ -207,7 +207,7 @@ am_status am_calc_chunks_files(am_matcher *h, size_t n_files, const void *const 
  * The reference hands calc_chunks a lazy iterator of decoded frames with a claimed length (mp3_reader.rs:13-66,
  * matcher/mod.rs:71-83).  A decoder thread calls am_stream_push with whatever it has decoded (host memory of any
  * kind, any piece size; the buffer may be reused as soon as the call returns); the library collects the frames in a
- * pinned ring, uploads them with one asynchronous copy per 32 MB and launches the transforms + peak search of a
+ * pinned ring, uploads them with one asynchronous copy per 8 MB and launches the transforms + peak search of a
  * segment of logical chunks as soon as its frames are complete, so matching and upload overlap decoding.
  * max_frames: upper bound of the stream length (the claimed length, mod.rs:78); the stream's true length is what has
  * been pushed when am_stream_finish is called.  Results equal am_calc_chunks on the concatenated frames.

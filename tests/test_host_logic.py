@@ -139,3 +139,26 @@ def test_integration_doc_matches_the_shim():
     sig = re.search(r"pub fn calc_chunks<.*?>>\(\n(.*?)\n\) ->", shim, re.S).group(1)
     assert [a.split(":")[0].strip() for a in sig.split(",") if a.strip()] == ["sr", "m_samples", "algo_with_sample", "scale", "config"]
     assert "_config_from" not in shim
+
+
+def test_calc_chunks_files_argument_checks():
+    """Host side of am_calc_chunks_files: one sample format and one memory space per call, sample-rate check first
+    (CliError::SampleRateMismatch, src/matcher/mod.rs:72); no device needed for the rejections."""
+    import numpy as np
+    import pytest
+    import audio_matcher_b200 as am
+    from audio_matcher_b200.matcher import CudaConvolve
+
+    class Handle:                      # stands in for a matcher: the checks run before the native call
+        sr = 8000
+        _h = None
+
+        def set_config(self, config):
+            raise AssertionError("must not be reached")
+
+    with pytest.raises(ValueError):
+        am.calc_chunks_files(44100, [np.zeros(8, np.int16)], Handle(), True, am.Config())
+    with pytest.raises(TypeError):
+        CudaConvolve._calc_files_raw(Handle(), [np.zeros(8, np.int16), np.zeros(8, np.float32)], True, 16)
+    buf, counts = CudaConvolve._calc_files_raw(Handle(), [], True, 16)
+    assert counts == []

@@ -73,6 +73,7 @@ SYMBOLS = {
     "am_matcher_set_progress": (C.c_int, [_VP, _VP, _VP]),
     "am_inverse_sample_auto_correlation": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "am_out_len": (_SZ, [_SZ, _SZ, C.c_int]),
+    "am_valid_len": (_SZ, [_SZ, _SZ]),
     "am_correlate": (C.c_int, [_VP, _VP, _SZ, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _SZ, C.c_int,
                                C.POINTER(_SZ)]),
     "am_num_chunks": (_SZ, [_VP, _SZ]),

@@ -868,6 +868,8 @@ size_t am_out_len(size_t n, size_t m, am_mode mode) {
     }
 }
 
+size_t am_valid_len(size_t n, size_t m) { return am_out_len(n, m, AM_MODE_VALID); }
+
 static am_status create_impl(const void *data, size_t m, size_t S, int fmt, uint32_t sr, const am_config *cfg,
                              am_matcher **out) {
     if (!out) return fail(AM_ERR_INVALID, "out is NULL");

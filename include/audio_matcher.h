@@ -155,6 +155,9 @@ am_status am_inverse_sample_auto_correlation(am_matcher *h, float *out);
 
 /* output length of a correlation of n stream samples with m snippet samples */
 size_t am_out_len(size_t n, size_t m, am_mode mode);
+/* the Valid case, V = n - m + 1 (0 when n < m): the outputs one logical chunk of n samples contributes
+ * (audio_matcher.rs:121) */
+size_t am_valid_len(size_t n, size_t m);
 
 /* CorrelateAlgo::correlate_with_sample (audio_matcher.rs:67-72): writes the correlation
  * (scaled by 1/sum(s^2) when scale != 0, audio_matcher.rs:73-75,306-308) to `out`.

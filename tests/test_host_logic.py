@@ -36,6 +36,7 @@ def test_out_len(native, orc):
     for n, m in [(20, 3), (4000, 50), (3, 3), (2, 3), (0, 3), (5, 0)]:
         for mode in (0, 1, 2):
             assert L.am_out_len(n, m, mode) == orc.out_len(n, m, mode)
+        assert L.am_valid_len(n, m) == orc.out_len(n, m, 2)
 
 
 def test_no_gpu_fails_loudly(native):
